@@ -1,0 +1,133 @@
+"""Sampler front-end: schedule / sampler strategy objects and the host-side scalar plan.
+
+Mirrors the L3/L2 interface of the reference (diffusion.py) for the one combination the
+QM wrappers select -- ``ADPM2Sampler(rho=1)`` + ``KarrasSchedule`` over ``KDiffusion_mod`` --
+but none of it runs a Python step loop: the objects only *describe* the run; the loop is a
+CUDA-graph-captured driver inside the C-ABI library (csrc/plan.cu).
+
+The scalar plan reproduces the reference's float32-tensor / Python-double mixing exactly:
+  KarrasSchedule.forward        diffusion.py:333-342
+  ADPM2Sampler.get_sigmas       diffusion.py:495-500   (sigma_up, sigma_down are doubles via math.sqrt,
+                                                         sigma_mid stays a float32 0-dim tensor)
+  ADPM2Sampler.step             diffusion.py:502-515
+  KDiffusion_mod.get_scale_weights / denoise_fn   diffusion.py:789-814
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from math import sqrt
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class KarrasSchedule:
+    """sigma_i = (smax^(1/rho) + i/(N-1) (smin^(1/rho) - smax^(1/rho)))^rho, padded with 0."""
+
+    def __init__(self, sigma_min: float, sigma_max: float, rho: float = 7.0):
+        self.sigma_min, self.sigma_max, self.rho = sigma_min, sigma_max, rho
+
+    def __call__(self, num_steps: int, device=None) -> torch.Tensor:
+        rho_inv = 1.0 / self.rho
+        i = torch.arange(num_steps, dtype=torch.float32)
+        s = (self.sigma_max ** rho_inv
+             + (i / (num_steps - 1)) * (self.sigma_min ** rho_inv - self.sigma_max ** rho_inv)) ** self.rho
+        return F.pad(s, pad=(0, 1), value=0.0)
+
+
+class ADPM2Sampler:
+    """DPM-2 ancestral sampler description (diffusion.py:486-524); ``alias`` check as diffusion.py:571-575."""
+
+    diffusion_aliases = ("k", "vk")
+
+    def __init__(self, rho: float = 1.0):
+        self.rho = rho
+
+    def get_sigmas(self, sigma: torch.Tensor, sigma_next: torch.Tensor):
+        r = self.rho
+        sigma_up = sqrt(sigma_next ** 2 * (sigma ** 2 - sigma_next ** 2) / sigma ** 2)
+        sigma_down = sqrt(sigma_next ** 2 - sigma_up ** 2)
+        sigma_mid = ((sigma ** (1 / r) + sigma_down ** (1 / r)) / 2) ** r
+        return sigma_up, sigma_down, sigma_mid
+
+
+# One row per denoiser call / per ADPM2 iteration.  Layout shared with include/mdt_b200.h
+# (struct mdt_iter_scalars): 2 x {c_in, c_noise, c_skip, c_out, inv-free sigma divisor} + update coefficients.
+ITER_SCALAR_FIELDS = (
+    "sigma", "c_in_a", "c_noise_a", "c_skip_a", "c_out_a",
+    "sigma_mid", "c_in_b", "c_noise_b", "c_skip_b", "c_out_b",
+    "dt_mid", "dt_down", "sigma_up",
+)
+
+
+def _scale_weights(sigma: torch.Tensor, sigma_data: float):
+    """KDiffusion_mod.get_scale_weights on a 1-element batch (diffusion.py:789-796)."""
+    sigmas = torch.full(size=(1,), fill_value=sigma)  # to_batch, diffusion.py:100
+    c_noise = torch.log(sigmas) * 0.25
+    s = sigmas.view(1, 1, 1)
+    c_skip = (sigma_data ** 2) / (s ** 2 + sigma_data ** 2)
+    c_out = s * sigma_data * (sigma_data ** 2 + s ** 2) ** -0.5
+    c_in = (s ** 2 + sigma_data ** 2) ** -0.5
+    return float(c_in), float(c_noise), float(c_skip), float(c_out)
+
+
+def build_iter_scalars(sigmas: torch.Tensor, num_steps: int, sampler: ADPM2Sampler, sigma_data: float) -> np.ndarray:
+    """Host plan: float32 table [num_steps-1, 13] of every scalar the fused step kernels need."""
+    sigmas = sigmas.detach().to("cpu", torch.float32)
+    rows: List[List[float]] = []
+    for i in range(num_steps - 1):
+        sig, sig_next = sigmas[i], sigmas[i + 1]
+        sigma_up, sigma_down, sigma_mid = sampler.get_sigmas(sig, sig_next)
+        sigma_mid = torch.as_tensor(sigma_mid, dtype=torch.float32)
+        a = _scale_weights(sig, sigma_data)
+        b = _scale_weights(sigma_mid, sigma_data)
+        dt_mid = float(sigma_mid - sig)            # diffusion.py:508  (float32 tensor arithmetic)
+        dt_down = float(sigma_down - sig)          # diffusion.py:512  (double - float32 tensor -> float32)
+        up = float(torch.ones((), dtype=torch.float32) * sigma_up)  # diffusion.py:514 scalar cast
+        rows.append([float(sig), *a, float(sigma_mid), *b, dt_mid, dt_down, up])
+    return np.asarray(rows, dtype=np.float32).reshape(max(num_steps - 1, 0), len(ITER_SCALAR_FIELDS))
+
+
+class _KDiffusionShell(nn.Module):
+    """Holds ``net`` under the name the reference gives it (KDiffusion_mod, diffusion.py:775-787)."""
+
+    alias = "k"
+
+    def __init__(self, net: nn.Module, sigma_data: float, dynamic_threshold: float = 0.0):
+        super().__init__()
+        if dynamic_threshold != 0.0:
+            raise NotImplementedError("dynamic thresholding (diffusion.py:78-88) is never enabled by the QM wrappers")
+        self.net = net
+        self.sigma_data = sigma_data
+        self.dynamic_threshold = dynamic_threshold
+
+
+class XDiffusion_x(nn.Module):
+    """Front-end shell with the reference's attribute layout (diffusion.py:706-767).
+
+    ``state_dict`` therefore carries ``net.*`` and ``diffusion.net.*`` aliases of the UNet
+    parameters exactly like the reference.  ``sample`` is wired by the owning wrapper.
+    """
+
+    def __init__(self, type: str, net: nn.Module, *, sigma_data: float, dynamic_threshold: float = 0.0,
+                 sigma_distribution=None):
+        super().__init__()
+        assert type == "k", f"type='{type}' must be 'k' on the accelerated path"
+        self.net = net
+        self.diffusion = _KDiffusionShell(net, sigma_data, dynamic_threshold)
+        self._runner = None  # set by the wrapper: callable(noise, num_steps, schedule, sampler, clamp, **kw)
+
+    def sample(self, noise, num_steps: int, sigma_schedule, sampler, clamp: bool, **kwargs):
+        assert self.diffusion.alias in sampler.diffusion_aliases, \
+            f"{sampler.__class__.__name__} incompatible with KDiffusion_mod"
+        assert num_steps is not None, "Parameter `num_steps` must be provided"
+        if self._runner is None:
+            raise RuntimeError("XDiffusion_x.sample needs an owning QMDiffusion/QMDiffusionForward wrapper")
+        return self._runner(noise=noise, num_steps=num_steps, sigma_schedule=sigma_schedule,
+                            sampler=sampler, clamp=clamp, **kwargs)
+
+    def forward(self, *a, **k):  # training loss: out of scope
+        raise NotImplementedError("training forward is outside the accelerated sampling path")

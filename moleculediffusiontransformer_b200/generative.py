@@ -1,0 +1,172 @@
+"""Drop-in task wrappers: ``QMDiffusion`` (inverse) and ``QMDiffusionForward`` (property predictor).
+
+Same constructor kwargs, same ``state_dict`` keys, same ``sample(sequences, device, cond_scale,
+timesteps, clamp)`` contract as the reference (generative.py:720-870, 33-180).  The body of
+``sample`` hands the conditioning matrix to a CUDA plan (plan.py -> csrc/): the conditioning
+encoder, the 63-iteration ADPM2 loop and the UNet all run inside the sm_100a library.  There
+is no eager / CPU fallback: without a CUDA device and the built extension ``sample`` raises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .diffusion import ADPM2Sampler, KarrasSchedule, XDiffusion_x
+from .unet_params import UNetCFG1dParams, XUNet1d
+
+
+class _FourierPE(nn.Module):
+    """Holds the ``inv_freq`` buffer of PositionalEncoding1D (transformer.py:3444-3454)."""
+
+    def __init__(self, channels: int):
+        super().__init__()
+        self.org_channels = channels
+        channels = int(np.ceil(channels / 2) * 2)
+        self.channels = channels
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, channels, 2).float() / channels))
+        self.register_buffer("inv_freq", inv_freq)
+
+
+class _QMBase(nn.Module):
+    _default_cond_scale = 1.0
+    _unet_kwargs: dict = {}
+
+    def __init__(self, max_length, channels, pred_dim, unet, context_embedding_max_length, unet_type,
+                 pos_emb_fourier, pos_emb_fourier_add, text_embed_dim, embed_dim_position):
+        super().__init__()
+        if unet_type != "cfg":
+            raise NotImplementedError("only unet_type='cfg' is on the accelerated path (generative.py:862-868 is not)")
+        self.unet_type = unet_type
+        self.fc1 = nn.Linear(1, text_embed_dim)
+        self.text_embed_dim = text_embed_dim
+        self.embed_dim_position = embed_dim_position
+        self.pos_emb_fourier = pos_emb_fourier
+        self.pos_emb_fourier_add = pos_emb_fourier_add
+        ctx_features = text_embed_dim
+        if pos_emb_fourier:
+            if not pos_emb_fourier_add:
+                ctx_features = text_embed_dim + embed_dim_position
+            self.p_enc_1d = _FourierPE(embed_dim_position)
+        self.max_length = max_length
+        self.pred_dim = pred_dim
+        if unet is not None:
+            if not isinstance(unet, UNetCFG1dParams):
+                raise TypeError("unet= must be a moleculediffusiontransformer_b200 XUNet1d(type='cfg', ...) instance")
+            self.unet = unet
+        else:
+            self.unet = XUNet1d(type="cfg", in_channels=pred_dim, channels=channels,
+                                context_embedding_features=ctx_features,
+                                context_embedding_max_length=context_embedding_max_length,
+                                **self._unet_kwargs)
+        self.diffusion = XDiffusion_x(type="k", net=self.unet, sigma_data=0.1, dynamic_threshold=0.0)
+        object.__setattr__(self.diffusion, "_runner", self._run_sampler)
+        self._plans = {}
+
+    # ------------------------------------------------------------------ plan management
+    def _plan_for(self, device: torch.device, precision: Optional[str] = None):
+        from .plan import SamplerPlan, default_precision
+
+        precision = precision or default_precision()
+        key = (str(device), precision)
+        plan = self._plans.get(key)
+        version = sum(p._version for p in self.parameters())
+        if plan is None or plan.weights_version != version:
+            if plan is not None:
+                plan.close()
+            plan = SamplerPlan(self, device, precision=precision)
+            plan.weights_version = version
+            self._plans[key] = plan
+        return plan
+
+    def _apply(self, fn, *a, **k):  # .to()/.cuda()/.float() invalidate packed weights
+        for p in self._plans.values():
+            p.close()
+        self._plans = {}
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        for p in self._plans.values():
+            p.close()
+        self._plans = {}
+        return super().load_state_dict(*a, **k)
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, sequences, output):
+        raise NotImplementedError("training loss (generative.py:812-833) is outside the accelerated sampling path")
+
+    def _run_sampler(self, *, noise, num_steps, sigma_schedule, sampler, clamp, embedding=None,
+                     embedding_scale=1.0, sequences=None, step_noise=None, seed=None, precision=None,
+                     return_tokens=False):
+        if sequences is None:
+            raise NotImplementedError(
+                "the accelerated path encodes the conditioning on the device; call model.sample(sequences, ...)")
+        device = noise.device if noise is not None else sequences.device
+        plan = self._plan_for(torch.device(device), precision)
+        return plan.sample(sequences, noise0=noise, step_noise=step_noise, num_steps=num_steps,
+                           sigma_schedule=sigma_schedule, sampler=sampler, clamp=clamp,
+                           cond_scale=float(embedding_scale), seed=seed, return_tokens=return_tokens)
+
+    def sample(self, sequences, device, cond_scale=None, timesteps=100, clamp=False, *,
+               noise=None, step_noise=None, seed=None, precision=None, return_tokens=False):
+        """Generate ``(B, pred_dim, max_length)`` float32 on ``device``.
+
+        Positional arguments are the reference's (generative.py:834 / :146).  Keyword-only extras:
+        ``noise`` / ``step_noise`` inject the initial and per-iteration noise tensors
+        (``(B,P,L)`` and ``(timesteps-1,B,P,L)``) for parity runs; otherwise the initial noise is
+        drawn from the CPU global generator exactly like the reference (generative.py:853) and the
+        ancestral noise comes from an in-kernel Philox stream keyed by (seed, sample index, step).
+        """
+        if cond_scale is None:
+            cond_scale = self._default_cond_scale
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("moleculediffusiontransformer_b200 runs on sm_100a CUDA devices only "
+                               f"(got device={device}); there is no CPU path")
+        b = sequences.shape[0]
+        if sequences.shape[1] > self.unet.fixed_embedding.max_length:
+            raise AssertionError("Input sequence length must be <= max_length")  # modules.py:1194-1195
+        if noise is None and seed is None:
+            noise = torch.randn(b, self.pred_dim, self.max_length)
+        if noise is not None:
+            noise = noise.to(device)
+        return self.diffusion.sample(
+            num_steps=timesteps, sampler=ADPM2Sampler(rho=1),
+            sigma_schedule=KarrasSchedule(sigma_min=0.001, sigma_max=9.0, rho=3.0), clamp=clamp,
+            noise=noise, embedding=None, embedding_scale=cond_scale, sequences=sequences.to(device),
+            step_noise=step_noise, seed=seed, precision=precision, return_tokens=return_tokens)
+
+    def inpaint(self, *a, **k):
+        raise NotImplementedError("inpainting (generative.py:871-914) is a 'next' row of the scope table")
+
+
+class QMDiffusion(_QMBase):
+    """Inverse model: 12 properties -> (pred_dim, max_length) token logits (generative.py:718-914)."""
+
+    _default_cond_scale = 7.5
+    _unet_kwargs = dict(pre_transformer=2, patch_size=1, multipliers=[1, 2, 4], factors=[4, 4],
+                        num_blocks=[3, 3], attentions=[4, 4], attention_heads=8, attention_features=64,
+                        attention_multiplier=2, attention_use_rel_pos=False)
+
+    def __init__(self, max_length=1024, channels=128, pred_dim=1, context_embedding_max_length=32,
+                 unet_type="cfg", pos_emb_fourier=True, pos_emb_fourier_add=False, text_embed_dim=1024,
+                 embed_dim_position=64, unet=None):
+        super().__init__(max_length, channels, pred_dim, unet, context_embedding_max_length, unet_type,
+                         pos_emb_fourier, pos_emb_fourier_add, text_embed_dim, embed_dim_position)
+
+
+class QMDiffusionForward(_QMBase):
+    """Forward model: SMILES token embedding -> property vector (generative.py:31-225)."""
+
+    _default_cond_scale = 1.0
+    _unet_kwargs = dict(patch_size=4, multipliers=[1, 2, 4], factors=[4, 4], num_blocks=[3, 3],
+                        attentions=[2, 2], attention_heads=8, attention_features=64,
+                        attention_multiplier=2, attention_use_rel_pos=False)
+
+    def __init__(self, max_length=1024, channels=128, pred_dim=1, unet=None, context_embedding_max_length=32,
+                 unet_type="cfg", pos_emb_fourier=True, pos_emb_fourier_add=False, text_embed_dim=1024,
+                 embed_dim_position=64):
+        super().__init__(max_length, channels, pred_dim, unet, context_embedding_max_length, unet_type,
+                         pos_emb_fourier, pos_emb_fourier_add, text_embed_dim, embed_dim_position)

@@ -1,0 +1,41 @@
+"""Seeded parity cases shared by oracle/make_golden.py and tests/ (inputs are regenerated from seeds)."""
+from __future__ import annotations
+
+import torch
+
+INV64 = dict(max_length=64, pred_dim=16, channels=64, unet_type="cfg", context_embedding_max_length=12,
+             pos_emb_fourier=True, pos_emb_fourier_add=False, text_embed_dim=64, embed_dim_position=64)
+FWD64 = dict(max_length=64, pred_dim=1, channels=64, unet_type="cfg", context_embedding_max_length=64,
+             pos_emb_fourier=True, pos_emb_fourier_add=False, text_embed_dim=64, embed_dim_position=64)
+WIDE = dict(max_length=128, pred_dim=32, channels=128, unet_type="cfg", context_embedding_max_length=12,
+            pos_emb_fourier=True, pos_emb_fourier_add=False, text_embed_dim=64, embed_dim_position=64)
+PAPER = dict(max_length=32, pred_dim=22, channels=128, unet_type="cfg", context_embedding_max_length=12,
+             pos_emb_fourier=True, pos_emb_fourier_add=False, text_embed_dim=64, embed_dim_position=64)
+
+# name -> (kind, ctor kwargs, model seed, data seed, batch, ctx_len, cond_scale, timesteps, clamp)
+CASES = {
+    "inv64_cs1":    ("inverse", INV64, 0, 1234, 4, 12, 1.0, 64, False),
+    "inv64_cs7p5":  ("inverse", INV64, 0, 1234, 4, 12, 7.5, 64, False),
+    "inv64_short_ctx_clamp": ("inverse", INV64, 0, 77, 3, 7, 2.0, 8, True),
+    "fwd64_cs1":    ("forward", FWD64, 0, 2, 4, 64, 1.0, 16, False),
+    "fwd64_cs2":    ("forward", FWD64, 0, 2, 2, 64, 2.0, 6, False),
+    "wide_cs7p5":   ("inverse", WIDE, 0, 3, 2, 12, 7.5, 6, False),
+    "paper_cs2":    ("inverse", PAPER, 0, 5, 2, 12, 2.0, 6, False),
+}
+
+
+def make_inputs(name: str):
+    kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES[name]
+    g = torch.Generator().manual_seed(dseed)
+    if kind == "forward":
+        # synthetic tokenised SMILES / 21 (generative.py:682-685): ragged lengths, zero padded
+        lens = torch.randint(1, 30, (b,), generator=g)
+        toks = torch.randint(1, 22, (b, n), generator=g).float()
+        toks = toks * (torch.arange(n)[None, :] < lens[:, None])
+        seq = toks / 21.0
+    else:
+        seq = torch.rand(b, n, generator=g) * 2 - 1
+    p, l = kw["pred_dim"], kw["max_length"]
+    noise0 = torch.randn(b, p, l, generator=g)
+    step_noise = torch.randn(steps - 1, b, p, l, generator=g)
+    return seq, noise0, step_noise

@@ -1,0 +1,52 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference in this container.
+
+    python -m oracle.make_golden            # all cases of oracle/cases.py
+
+Inputs are regenerated from seeds (oracle/cases.py); weights from torch.manual_seed(model seed).
+Only outputs (and a few UNet-level taps) are stored, so fixtures stay a few tens of KB each.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import reference_loader as rl  # noqa: E402
+from oracle.cases import CASES, make_inputs  # noqa: E402
+
+
+def main(names=None):
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    models = {}
+    for name in (names or CASES):
+        kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES[name]
+        key = (kind, tuple(sorted(kw.items())), mseed)
+        if key not in models:
+            models[key] = rl.build_model(kind, seed=mseed, **kw)
+        m = models[key]
+        seq, noise0, step_noise = make_inputs(name)
+        with rl.injected_noise(noise0, step_noise):
+            out = m.sample(seq, "cpu", cond_scale=cs, timesteps=steps, clamp=clamp)
+        # one raw UNet evaluation (conditional branch) at sigma = 1.0 for kernel-level parity
+        with torch.no_grad():
+            x = seq.float().unsqueeze(2)
+            emb = m.GELUact(m.fc1(x))
+            emb = torch.cat((emb, m.p_enc_1d(emb)), 2)
+            t = torch.full((b,), 0.37)
+            net = m.unet(noise0, t, embedding=emb, embedding_scale=cs)
+        pcount = sum(p.numel() for p in m.unet.parameters()) + m.fc1.weight.numel() + m.fc1.bias.numel()
+        psum = float(sum(p.double().sum() for p in {id(p): p for p in m.parameters()}.values()))
+        np.savez_compressed(
+            os.path.join(ROOT, "tests", "golden", f"{name}.npz"),
+            out=out.numpy(), net=net.numpy(), emb=emb.numpy(), param_sum=np.float64(psum),
+            param_count=np.int64(pcount), torch_version=np.bytes_(torch.__version__.encode()))
+        print(f"{name}: out.sum={out.double().sum():.6f} net.sum={net.double().sum():.6f} params={pcount}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or None)

@@ -1,0 +1,65 @@
+"""The oracle (oracle/unet_oracle.py) against fixtures produced by the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import unet_oracle as orc
+from oracle.cases import CASES, make_inputs
+
+FAST = ["inv64_cs1", "inv64_short_ctx_clamp", "fwd64_cs2", "paper_cs2"]
+
+
+def _sd_cfg(model):
+    sd = {k: v.detach() for k, v in model.state_dict().items() if not k.startswith("diffusion.")}
+    return sd, model.unet.cfg.to_dict()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_seeded_init_matches_reference(name, model_cache):
+    kind, kw, mseed, *_ = CASES[name]
+    m = model_cache(kind, kw, mseed)
+    g = golden(name)
+    uniq = {id(p): p for p in m.parameters()}
+    assert sum(p.numel() for p in uniq.values()) == int(g["param_count"])
+    psum = float(sum(p.detach().double().sum() for p in uniq.values()))
+    assert psum == pytest.approx(float(g["param_sum"]), rel=0, abs=1e-9)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_unet_eval_matches_reference(name, model_cache):
+    kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES[name]
+    m = model_cache(kind, kw, mseed)
+    sd, cfg = _sd_cfg(m)
+    seq, noise0, _ = make_inputs(name)
+    g = golden(name)
+    with torch.no_grad():
+        emb = orc.encode_conditioning(sd, seq)
+        assert np.array_equal(emb.numpy(), g["emb"])
+        net = orc.unet_cfg_forward(sd, cfg, noise0, torch.full((b,), 0.37), emb, cs)
+    # identical op sequence on the same CPU kernels: expect (near) bit equality
+    assert orc.rel_l2(net, torch.from_numpy(g["net"])) < 1e-6
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_full_sample_matches_reference(name, model_cache):
+    kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES[name]
+    m = model_cache(kind, kw, mseed)
+    sd, cfg = _sd_cfg(m)
+    seq, noise0, step_noise = make_inputs(name)
+    out = orc.sample(sd, cfg, seq, noise0, step_noise, cs, steps, clamp)
+    ref = torch.from_numpy(golden(name)["out"])
+    assert out.shape == ref.shape == (b, kw["pred_dim"], kw["max_length"])
+    assert orc.rel_l2(out, ref) < 1e-5
+    assert (orc.tokens_from_logits(out) == orc.tokens_from_logits(ref)).float().mean() == 1.0
+
+
+def test_survey_self_check_values():
+    """SURVEY.md 8(c) self-check numbers for the README model (seed 0, generator 1234)."""
+    g = golden("inv64_cs1")["out"]
+    assert float(g.astype(np.float64).sum()) == pytest.approx(191.704454, abs=2e-4)
+    assert np.allclose(g[0, 0, :4], [0.092168, 0.032204, 0.119221, 0.249968], atol=2e-6)
+    toks = g.transpose(0, 2, 1).argmax(2)
+    assert toks[0, :16].tolist() == [8, 11, 1, 11, 9, 13, 14, 5, 1, 9, 9, 3, 11, 0, 11, 3]
+    g2 = golden("inv64_cs7p5")["out"]
+    assert float(g2.astype(np.float64).sum()) == pytest.approx(289.317932, abs=4e-4)
