@@ -1,0 +1,142 @@
+// kernels.cuh -- parameter blocks and launcher declarations shared by the CUDA translation units.
+//
+// Activation layout everywhere inside the library: TOKEN-MAJOR fp32, i.e. a tensor the
+// reference holds as (b, C, L) lives in HBM as [b * L + l][c] (row = one position of one
+// sample, channels contiguous).  All contractions are then row-major GEMMs with M = B_eff * L.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mdt {
+
+// ---------------------------------------------------------------------------------------------
+// A-operand loader: describes how element (m, k) of the GEMM's left operand is produced from
+// activations in HBM.  It covers plain linear layers, k-tap strided Conv1d as implicit GEMM
+// (zero padding at SAMPLE boundaries), channel concatenation of two sources (skip connections),
+// LayerNorm / GroupNorm normalisation on load, per-channel affine (GroupNorm gamma/beta with the
+// FiLM scale/shift folded in, per denoiser call) and SiLU.
+//   k = tap * C + c ;  m = b * L_out + lo ;  li = lo * stride + tap - pad
+//   v = src(b * L_in + li, c) [* scale1 for the second segment]
+//   v = (v - mean) * rstd            if stats   (mode 1: per source row; mode 2: per (sample, group))
+//   v = v * aff[c] + aff[C + c]      if aff
+//   v = silu(v)                      if silu
+//   v = 0 where li is outside [0, L_in)   (padding applies to the transformed tensor, modules.py:105-122)
+// ---------------------------------------------------------------------------------------------
+struct ALoad {
+  const float* src0;
+  const float* src1;
+  int c0, c1, C;
+  float scale1;
+  int L_in, L_out, taps, stride, pad;
+  const float* stats;
+  int stats_mode;  // 0 none, 1 row, 2 (sample, group)
+  int groups, cpg;
+  const float* aff;
+  int aff_call_stride;  // floats per call index; 0 = static table
+  const int* call_idx;  // device scalar: current denoiser call (may be null)
+  int silu;
+};
+
+struct GemmParams {
+  ALoad a;
+  const float* W;     // [N][K] fp32, K = taps * C contiguous
+  const void* Wtc;    // same matrix pre-converted for the tensor-core kernel (tf32 bits or bf16), or null
+  const float* bias;  // [N] or null
+  int M, N, K;
+  int act;            // 0 none, 1 exact GELU
+  const float* res;   // residual [M][ldres] or null (may alias C)
+  int ldres;
+  float* C;
+  int ldc;
+};
+
+struct AttnParams {
+  const float* q; int ldq;            // [B*nq][ldq], head h at columns h*d..
+  const float* k; const float* v;     // per-sample blocks: row (b*nk + j), leading dim ldkv
+  int ldkv; long long kv_sample_stride;  // floats between consecutive samples' K/V blocks
+  const float* k_null; const float* v_null;  // shared K/V for samples >= n_cond (classifier-free null branch)
+  int n_cond;
+  float* o; int ldo;
+  int B, nq, nk, heads, d;
+  float scale;
+};
+
+struct NormStatsParams {
+  const float* src0; const float* src1;
+  int c0, c1; float scale1;
+  int L;        // positions per sample (GroupNorm) -- unused for row mode
+  int groups;   // GroupNorm groups
+  float eps;
+  float* stats; // out: [rows][2] or [B][groups][2]   (mean, rstd)
+  int rows;     // row mode: number of rows; group mode: number of samples
+};
+
+// Per-iteration scalars as laid out in include/mdt_b200.h (mdt_iter_scalars).
+struct IterScalars {
+  float sigma, c_in_a, c_noise_a, c_skip_a, c_out_a;
+  float sigma_mid, c_in_b, c_noise_b, c_skip_b, c_out_b;
+  float dt_mid, dt_down, sigma_up;
+};
+
+struct StepParams {
+  const IterScalars* iters;  // device table [n_iters]
+  const int* call_idx;       // device scalar; iteration = call_idx / 2
+  const float* net;          // network output, token-major [B_eff*L][P]; rows [0,B*L) cond, [B*L, 2*B*L) null
+  float* x;                  // sampler state, token-major [B*L][P]
+  float* xmid;               // midpoint state
+  float* xin;                // next network input, token-major [B_eff*L][P]  (both halves written)
+  const float* noise;        // injected ancestral noise (B,P,L) for this iteration, or null => Philox
+  long long noise_iter_stride;  // floats between iterations in the injected noise tensor
+  unsigned long long seed, sample_offset;
+  float cond_scale;
+  int cfg;                   // 1 => two branches
+  int B, P, L;
+  int n_iters;
+  float* out;                // final (B,P,L) result written when the last iteration completes (may be null)
+  unsigned char* tokens;     // final argmax tokens [B][L] (may be null)
+  int clamp;
+};
+
+// ---- launchers (kernels.cu) -------------------------------------------------------------------
+// per-device one-time function attributes (call after cudaSetDevice, outside stream capture)
+cudaError_t init_kernels();
+cudaError_t init_gemm_tc();
+cudaError_t launch_gemm_fp32(const GemmParams& p, cudaStream_t s);
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t s);
+cudaError_t launch_groupnorm_stats(const NormStatsParams& p, cudaStream_t s);
+cudaError_t launch_rownorm_stats(const NormStatsParams& p, cudaStream_t s);
+// out[b, o, co] = bias[co] + sum_j Y[b, i_j, k_j * Cout + co] (+ add[b, o, co]);  ConvTranspose1d(k=2f, s=f, p=f/2)
+cudaError_t launch_upsample_gather(const float* Y, const float* bias, const float* add, float* out, int B, int Lin,
+                                   int Cout, int f, cudaStream_t s);
+// Patcher / Unpatcher index maps (modules.py:230, 255): to_patched: [B, L*p, C] -> [B, L, C*p]
+cudaError_t launch_patch_permute(const float* in, float* out, int B, int L, int C, int p, int to_patched,
+                                 cudaStream_t s);
+// conditioning encoder (generative.py:838-850): emb[b, i, :] = [gelu(w * s + beta) | PE(i)] (or sum)
+cudaError_t launch_encode_cond(const float* seq, const float* w, const float* bias, const float* inv_freq,
+                               float* emb, int B, int n, int text_dim, int pos_dim, int add, cudaStream_t s);
+// time features (modules.py:554-559): out[r, :] = [t, sin(2 pi w t), cos(2 pi w t)], t = c_noise of call r
+cudaError_t launch_time_features(const float* t, const float* w, float* out, int rows, int half, cudaStream_t s);
+// FiLM fold: aff[r][c] = gamma[c] * (1 + ss[r][c]);  aff[r][C + c] = beta[c] * (1 + ss[r][c]) + ss[r][C + c]
+cudaError_t launch_film_fold(const float* ss, const float* gamma, const float* beta, float* aff, int rows, int C,
+                             cudaStream_t s);
+cudaError_t launch_step_init(const float* noise0, float* x, float* xin, const IterScalars* iters,
+                             unsigned long long seed, unsigned long long sample_offset, int B, int P, int L,
+                             int cfg, cudaStream_t s);
+cudaError_t launch_step_update(int which, const StepParams& p, cudaStream_t s);
+cudaError_t launch_finalize(const float* x, float* out, unsigned char* tokens, int B, int P, int L, int clamp,
+                            cudaStream_t s);
+cudaError_t launch_set_int(int* dst, int v, cudaStream_t s);
+cudaError_t launch_add_int(int* dst, int v, cudaStream_t s);
+// (B,P,L) <-> token-major [B*L][P], with optional duplication into a second half (classifier-free null rows)
+cudaError_t launch_to_token_major(const float* in, float* out, int B, int P, int L, float mul, int dup,
+                                  cudaStream_t s);
+cudaError_t launch_cfg_mix_to_bpl(const float* net, float* out, int B, int P, int L, float cond_scale, int cfg,
+                                  cudaStream_t s);
+
+// ---- tensor-core GEMM (gemm_tc.cu) --------------------------------------------------------------
+// kind: 1 = tf32, 2 = bf16.  Wtc must hold the weights pre-converted by convert_weights_tc().
+cudaError_t launch_gemm_tc(const GemmParams& p, int kind, cudaStream_t s);
+cudaError_t convert_weights_tc(const float* W, void* Wtc, long long n, int kind, cudaStream_t s);
+bool gemm_tc_supported(const GemmParams& p);
+
+}  // namespace mdt

@@ -1,0 +1,1033 @@
+// plan.cu -- host side of the C ABI: weight repacking, the UNet op program, the ADPM2 step driver.
+//
+// A plan turns the reference state_dict into kernel-native weight layouts once, builds a flat
+// list of kernel launches ("program") for one denoiser-network evaluation, and drives the
+// (timesteps - 1)-iteration ADPM2 loop entirely on the device: every scalar the loop needs
+// lives in a device table indexed by a device-side call counter, so one captured CUDA graph of
+// a single iteration is replayed for the whole run with no host synchronisation.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/mdt_b200.h"
+#include "kernels.cuh"
+
+using namespace mdt;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+struct MdtError {
+  int code;
+  std::string msg;
+};
+[[noreturn]] static void raise(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  throw MdtError{code, buf};
+}
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) raise(MDT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// program representation
+// ------------------------------------------------------------------------------------------------
+enum OpType { OP_GEMM, OP_GN_STATS, OP_ROW_STATS, OP_ATTN, OP_UPGATHER, OP_PERMUTE };
+
+struct Op {
+  OpType type = OP_GEMM;
+  int rps = 0;  // output rows per sample (GEMM M = B_eff * rps; row stats rows = B_eff * rps)
+  GemmParams g{};
+  NormStatsParams ns{};
+  AttnParams at{};
+  bool cross = false;  // attention reads the precomputed conditioning K/V
+  int cross_layer = -1;
+  // upsample gather / permute
+  const float* in0 = nullptr; const float* in1 = nullptr; const float* in2 = nullptr; float* out = nullptr;
+  int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+  // debug tap after this op
+  std::string tap;
+  const float* tap_ptr = nullptr;
+  int tap_rps = 0, tap_c = 0;
+  bool per_sample_fixed = false;  // op independent of batch (time / null-context programs use explicit M)
+};
+
+struct Film {   // one ResnetBlock1d's FiLM table
+  const float* w_ss; const float* b_ss;  // Linear(mapping -> 2C)
+  const float* gamma; const float* beta; // block2.groupnorm affine
+  int C;
+  float* ss;   // [max_calls][2C] raw scale|shift
+  float* aff;  // [max_calls][2C] folded (gamma * (1 + scale), beta * (1 + scale) + shift)
+};
+
+struct CrossLayer {
+  const float* wkv; const float* bkv;  // folded norm_context -> to_kv  [2*Hd][F], [2*Hd]
+  float* kv_cond;                      // [max_batch * n_ctx_max][2*Hd]
+  float* kv_null;                      // [n_ctx_max][2*Hd]
+};
+
+struct mdt_plan {
+  mdt_config cfg{};
+  int device = 0;
+  int prec = 0;
+  int max_calls = 0;
+  std::unordered_map<std::string, std::pair<const float*, int64_t>> tensors;
+  // device slab for weights
+  char* wslab = nullptr; size_t wcap = 0, wused = 0;
+  std::vector<void*> allocs;  // activation buffers
+  size_t act_bytes = 0;
+  long long launches = 0;
+
+  // model dims
+  int P = 0, L0 = 0, Hd = 0, F = 0, Bmax = 0, Beff_max = 0;
+  size_t S_act = 0;
+
+  // programs
+  std::vector<Op> unet;
+  std::vector<Film> films;
+  std::vector<CrossLayer> cross;
+  // act pool
+  std::vector<float*> pool_free;
+  // named buffers
+  float *xin = nullptr, *net_out = nullptr, *x = nullptr, *xmid = nullptr;
+  float *emb = nullptr, *emb_stats = nullptr, *emb_null = nullptr, *emb_null_stats = nullptr;
+  float *qkv = nullptr, *att = nullptr, *qc = nullptr, *ff = nullptr, *upy = nullptr;
+  float *gn_stats = nullptr, *row_stats = nullptr;
+  // time path
+  float *t_calls = nullptr, *t_feat = nullptr, *t_a = nullptr, *t_b = nullptr, *t_map = nullptr;
+  const float *w_time_freq = nullptr, *w_time = nullptr, *b_time = nullptr, *w_map0 = nullptr, *b_map0 = nullptr,
+              *w_map2 = nullptr, *b_map2 = nullptr;
+  // encoder
+  const float *w_fc1 = nullptr, *b_fc1 = nullptr, *inv_freq = nullptr, *w_null_emb = nullptr;
+  // step driver
+  IterScalars* d_iters = nullptr;
+  IterScalars* h_iters = nullptr;  // pinned
+  float* h_tcalls = nullptr;       // pinned
+  int* d_call = nullptr;
+  int n_ctx_cur = 0;
+  // graph cache: key (Bc, n_ctx, cfg, has_step_noise)
+  struct GraphEntry { cudaGraphExec_t exec; };
+  std::map<std::vector<long long>, GraphEntry> graphs;
+  bool use_graph = true;
+  // taps
+  bool taps_on = false;
+  std::map<std::string, std::vector<float>> tap_store;
+};
+
+// ------------------------------------------------------------------------------------------------
+// builder
+// ------------------------------------------------------------------------------------------------
+struct Src {  // activation source: up to two channel segments
+  const float* p0; int c0; const float* p1; int c1; float scale1;
+  int C() const { return c0 + c1; }
+};
+
+struct Builder {
+  mdt_plan& pl;
+  explicit Builder(mdt_plan& p) : pl(p) {}
+
+  // ---- state_dict access
+  const float* T(const std::string& name, int64_t numel) {
+    auto it = pl.tensors.find(name);
+    if (it == pl.tensors.end()) raise(MDT_ERR_MISSING, "state_dict tensor '%s' is missing", name.c_str());
+    if (it->second.second != numel)
+      raise(MDT_ERR_MISSING, "state_dict tensor '%s' has %lld elements, expected %lld", name.c_str(),
+            (long long)it->second.second, (long long)numel);
+    return it->second.first;
+  }
+  bool has(const std::string& name) { return pl.tensors.count(name) != 0; }
+
+  // ---- device weight slab
+  float* upload(const float* host, size_t n) {
+    const size_t bytes = (n * sizeof(float) + 255) & ~(size_t)255;
+    if (pl.wused + bytes > pl.wcap) raise(MDT_ERR_OOM, "weight slab exhausted (%zu + %zu > %zu)", pl.wused, bytes, pl.wcap);
+    float* d = reinterpret_cast<float*>(pl.wslab + pl.wused);
+    pl.wused += bytes;
+    CK(cudaMemcpy(d, host, n * sizeof(float), cudaMemcpyHostToDevice));
+    return d;
+  }
+  float* upload(const std::vector<float>& v) { return upload(v.data(), v.size()); }
+  void* slab_alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (pl.wused + bytes > pl.wcap) raise(MDT_ERR_OOM, "weight slab exhausted");
+    void* d = pl.wslab + pl.wused;
+    pl.wused += bytes;
+    return d;
+  }
+  // tensor-core copy of a packed [N][K] matrix (tf32-rounded fp32 bits or bf16), when the mode needs it
+  const void* tc_copy(const float* dW, size_t n) {
+    if (pl.prec == MDT_PREC_FP32) return nullptr;
+    void* d = slab_alloc(n * (pl.prec == MDT_PREC_BF16 ? 2 : 4));
+    CK(convert_weights_tc(dW, d, (long long)n, pl.prec, 0));
+    return d;
+  }
+
+  // ---- activation buffers
+  float* dalloc(size_t floats) {
+    void* p = nullptr;
+    const size_t bytes = floats * sizeof(float);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) raise(MDT_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    pl.allocs.push_back(p);
+    pl.act_bytes += bytes;
+    return reinterpret_cast<float*>(p);
+  }
+  float* acquire() {
+    if (!pl.pool_free.empty()) { float* p = pl.pool_free.back(); pl.pool_free.pop_back(); return p; }
+    return dalloc(pl.S_act * pl.Beff_max);
+  }
+  void release(const float* p) { pl.pool_free.push_back(const_cast<float*>(p)); }
+
+  // ---- weight packing helpers (host)
+  // Conv1d weight [N][C][taps] -> [N][taps*C]  (k = tap*C + c)
+  std::vector<float> pack_conv(const float* w, int N, int C, int taps) {
+    std::vector<float> o((size_t)N * C * taps);
+    for (int n = 0; n < N; ++n)
+      for (int c = 0; c < C; ++c)
+        for (int t = 0; t < taps; ++t) o[((size_t)n * taps + t) * C + c] = w[((size_t)n * C + c) * taps + t];
+    return o;
+  }
+  // y = W (x * gamma + beta) + b  ==>  W' = W diag(gamma), b' = b + W beta
+  void fold_affine(std::vector<float>& W, std::vector<float>& b, int N, int K, const float* gamma, const float* beta) {
+    for (int n = 0; n < N; ++n) {
+      double acc = 0.0;
+      for (int k = 0; k < K; ++k) {
+        acc += (double)W[(size_t)n * K + k] * (double)beta[k];
+        W[(size_t)n * K + k] *= gamma[k];
+      }
+      b[n] = (float)((double)b[n] + acc);
+    }
+  }
+
+  // ---- op emitters
+  ALoad make_aload(const Src& s, int L_in, int L_out, int taps, int stride, int pad) {
+    ALoad a{};
+    a.src0 = s.p0; a.src1 = s.p1; a.c0 = s.c0; a.c1 = s.c1; a.C = s.c0 + s.c1; a.scale1 = s.scale1;
+    a.L_in = L_in; a.L_out = L_out; a.taps = taps; a.stride = stride; a.pad = pad;
+    a.stats = nullptr; a.stats_mode = 0; a.groups = 1; a.cpg = a.C; a.aff = nullptr; a.aff_call_stride = 0;
+    a.call_idx = nullptr; a.silu = 0;
+    return a;
+  }
+  Op& emit(std::vector<Op>& prog, const Op& op) { prog.push_back(op); return prog.back(); }
+
+  Op gemm_op(const ALoad& a, const float* dW, const void* dWtc, const float* dbias, int N, int act, const float* res,
+             float* out, int rps) {
+    Op op; op.type = OP_GEMM; op.rps = rps;
+    op.g.a = a; op.g.W = dW; op.g.Wtc = dWtc; op.g.bias = dbias; op.g.M = 0; op.g.N = N; op.g.K = a.taps * a.C;
+    op.g.act = act; op.g.res = res; op.g.ldres = N; op.g.C = out; op.g.ldc = N;
+    return op;
+  }
+  void gn_stats(std::vector<Op>& prog, const Src& s, int L, int groups, float eps) {
+    Op op; op.type = OP_GN_STATS;
+    op.ns.src0 = s.p0; op.ns.src1 = s.p1; op.ns.c0 = s.c0; op.ns.c1 = s.c1; op.ns.scale1 = s.scale1;
+    op.ns.L = L; op.ns.groups = groups; op.ns.eps = eps; op.ns.stats = pl.gn_stats; op.ns.rows = 0;
+    if (s.C() % groups) raise(MDT_ERR_INVALID, "GroupNorm: %d channels not divisible by %d groups", s.C(), groups);
+    emit(prog, op);
+  }
+  void row_stats(std::vector<Op>& prog, const float* src, int C, int rps, float* stats) {
+    Op op; op.type = OP_ROW_STATS; op.rps = rps;
+    op.ns.src0 = src; op.ns.src1 = nullptr; op.ns.c0 = C; op.ns.c1 = 0; op.ns.scale1 = 1.f; op.ns.L = 1; op.ns.groups = 1;
+    op.ns.eps = 1e-5f; op.ns.stats = stats; op.ns.rows = 0;
+    emit(prog, op);
+  }
+  void set_tap(std::vector<Op>& prog, const std::string& name, const float* ptr, int rps, int c) {
+    Op& op = prog.back(); op.tap = name; op.tap_ptr = ptr; op.tap_rps = rps; op.tap_c = c;
+  }
+
+  // ResnetBlock1d (modules.py:145-205).  Returns the output buffer (acquired from the pool).
+  float* resnet(std::vector<Op>& prog, const std::string& pre, const Src& in, int L, int Cout, int groups) {
+    const int Cin = in.C();
+    const int M = pl.cfg.mapping_features;
+    // block1: GN(groups) -> SiLU -> conv3
+    std::vector<float> aff1(2 * (size_t)Cin);
+    memcpy(aff1.data(), T(pre + "block1.groupnorm.weight", Cin), Cin * sizeof(float));
+    memcpy(aff1.data() + Cin, T(pre + "block1.groupnorm.bias", Cin), Cin * sizeof(float));
+    const float* d_aff1 = upload(aff1);
+    auto w1 = pack_conv(T(pre + "block1.project.weight", (int64_t)Cout * Cin * 3), Cout, Cin, 3);
+    const float* d_w1 = upload(w1);
+    const float* d_b1 = upload(T(pre + "block1.project.bias", Cout), Cout);
+    gn_stats(prog, in, L, groups, 1e-5f);
+    float* h1 = acquire();
+    {
+      ALoad a = make_aload(in, L, L, 3, 1, 1);
+      a.stats = pl.gn_stats; a.stats_mode = 2; a.groups = groups; a.cpg = Cin / groups; a.aff = d_aff1; a.silu = 1;
+      emit(prog, gemm_op(a, d_w1, tc_copy(d_w1, w1.size()), d_b1, Cout, 0, nullptr, h1, L));
+    }
+    // FiLM table of this block
+    Film f{};
+    f.w_ss = upload(T(pre + "to_scale_shift.to_scale_shift.1.weight", (int64_t)2 * Cout * M), (size_t)2 * Cout * M);
+    f.b_ss = upload(T(pre + "to_scale_shift.to_scale_shift.1.bias", 2 * Cout), 2 * Cout);
+    f.gamma = upload(T(pre + "block2.groupnorm.weight", Cout), Cout);
+    f.beta = upload(T(pre + "block2.groupnorm.bias", Cout), Cout);
+    f.C = Cout;
+    f.ss = dalloc((size_t)pl.max_calls * 2 * Cout);
+    f.aff = dalloc((size_t)pl.max_calls * 2 * Cout);
+    pl.films.push_back(f);
+    // residual path
+    float* out = acquire();
+    const float* res;
+    if (has(pre + "to_out.weight")) {
+      const float* d_wo = upload(T(pre + "to_out.weight", (int64_t)Cout * Cin), (size_t)Cout * Cin);
+      const float* d_bo = upload(T(pre + "to_out.bias", Cout), Cout);
+      ALoad a = make_aload(in, L, L, 1, 1, 0);
+      emit(prog, gemm_op(a, d_wo, tc_copy(d_wo, (size_t)Cout * Cin), d_bo, Cout, 0, nullptr, out, L));
+      res = out;
+    } else {
+      if (in.c1 != 0 || Cin != Cout) raise(MDT_ERR_INVALID, "resnet '%s': identity skip needs Cin == Cout", pre.c_str());
+      res = in.p0;
+    }
+    // block2: GN -> FiLM -> SiLU -> conv3, + residual
+    Src hs{h1, Cout, nullptr, 0, 1.f};
+    gn_stats(prog, hs, L, groups, 1e-5f);
+    auto w2 = pack_conv(T(pre + "block2.project.weight", (int64_t)Cout * Cout * 3), Cout, Cout, 3);
+    const float* d_w2 = upload(w2);
+    const float* d_b2 = upload(T(pre + "block2.project.bias", Cout), Cout);
+    {
+      ALoad a = make_aload(hs, L, L, 3, 1, 1);
+      a.stats = pl.gn_stats; a.stats_mode = 2; a.groups = groups; a.cpg = Cout / groups;
+      a.aff = f.aff; a.aff_call_stride = 2 * Cout; a.call_idx = pl.d_call; a.silu = 1;
+      emit(prog, gemm_op(a, d_w2, tc_copy(d_w2, w2.size()), d_b2, Cout, 0, res, out, L));
+    }
+    release(h1);
+    return out;
+  }
+
+  // Transformer1d (modules.py:469-524).  ctx_features == 0 -> self-attention only.
+  float* transformer(std::vector<Op>& prog, const std::string& pre, const float* x, int L, int C, bool with_ctx) {
+    const int Hd = pl.Hd, heads = pl.cfg.heads, d = pl.cfg.head_features, F = pl.F;
+    // to_in: GroupNorm(32, eps 1e-6) folded into the 1x1 conv
+    std::vector<float> wi(T(pre + "to_in.1.weight", (int64_t)C * C), T(pre + "to_in.1.weight", (int64_t)C * C) + (size_t)C * C);
+    std::vector<float> bi(T(pre + "to_in.1.bias", C), T(pre + "to_in.1.bias", C) + C);
+    fold_affine(wi, bi, C, C, T(pre + "to_in.0.weight", C), T(pre + "to_in.0.bias", C));
+    const float* d_wi = upload(wi); const float* d_bi = upload(bi);
+    Src xs{x, C, nullptr, 0, 1.f};
+    gn_stats(prog, xs, L, 32, 1e-6f);
+    float* t = acquire();
+    {
+      ALoad a = make_aload(xs, L, L, 1, 1, 0);
+      a.stats = pl.gn_stats; a.stats_mode = 2; a.groups = 32; a.cpg = C / 32;
+      emit(prog, gemm_op(a, d_wi, tc_copy(d_wi, wi.size()), d_bi, C, 0, nullptr, t, L));
+    }
+    Src ts{t, C, nullptr, 0, 1.f};
+    for (int i = 0; has(pre + "blocks." + std::to_string(i) + ".attention.to_q.weight"); ++i) {
+      const std::string bp = pre + "blocks." + std::to_string(i) + ".";
+      // ---- self attention: fused QKV projection on LN statistics shared by norm / norm_context
+      {
+        const std::string ap = bp + "attention.";
+        std::vector<float> w((size_t)3 * Hd * C), b((size_t)3 * Hd, 0.f);
+        memcpy(w.data(), T(ap + "to_q.weight", (int64_t)Hd * C), (size_t)Hd * C * sizeof(float));
+        memcpy(w.data() + (size_t)Hd * C, T(ap + "to_kv.weight", (int64_t)2 * Hd * C), (size_t)2 * Hd * C * sizeof(float));
+        {
+          std::vector<float> wq(w.begin(), w.begin() + (size_t)Hd * C), bq(Hd, 0.f);
+          fold_affine(wq, bq, Hd, C, T(ap + "norm.weight", C), T(ap + "norm.bias", C));
+          std::vector<float> wkv(w.begin() + (size_t)Hd * C, w.end()), bkv(2 * Hd, 0.f);
+          fold_affine(wkv, bkv, 2 * Hd, C, T(ap + "norm_context.weight", C), T(ap + "norm_context.bias", C));
+          std::copy(wq.begin(), wq.end(), w.begin()); std::copy(wkv.begin(), wkv.end(), w.begin() + (size_t)Hd * C);
+          std::copy(bq.begin(), bq.end(), b.begin()); std::copy(bkv.begin(), bkv.end(), b.begin() + Hd);
+        }
+        const float* d_w = upload(w); const float* d_b = upload(b);
+        row_stats(prog, t, C, L, pl.row_stats);
+        ALoad a = make_aload(ts, L, L, 1, 1, 0);
+        a.stats = pl.row_stats; a.stats_mode = 1;
+        emit(prog, gemm_op(a, d_w, tc_copy(d_w, w.size()), d_b, 3 * Hd, 0, nullptr, pl.qkv, L));
+        Op at; at.type = OP_ATTN;
+        at.at.q = pl.qkv; at.at.ldq = 3 * Hd; at.at.k = pl.qkv + Hd; at.at.v = pl.qkv + 2 * Hd; at.at.ldkv = 3 * Hd;
+        at.at.kv_sample_stride = (long long)L * 3 * Hd; at.at.k_null = nullptr; at.at.v_null = nullptr; at.at.n_cond = 0;
+        at.at.o = pl.att; at.at.ldo = Hd; at.at.nq = L; at.at.nk = L; at.at.heads = heads; at.at.d = d;
+        at.at.scale = 1.0f / sqrtf((float)d);
+        emit(prog, at);
+        const float* d_wo = upload(T(ap + "attention.to_out.weight", (int64_t)C * Hd), (size_t)C * Hd);
+        const float* d_bo = upload(T(ap + "attention.to_out.bias", C), C);
+        Src as{pl.att, Hd, nullptr, 0, 1.f};
+        emit(prog, gemm_op(make_aload(as, L, L, 1, 1, 0), d_wo, tc_copy(d_wo, (size_t)C * Hd), d_bo, C, 0, t, t, L));
+      }
+      // ---- cross attention onto the conditioning embedding (K/V are loop invariant: precomputed per sample)
+      if (has(bp + "cross_attention.to_q.weight")) {
+        if (!with_ctx) raise(MDT_ERR_INVALID, "unexpected cross_attention under '%s'", bp.c_str());
+        const std::string ap = bp + "cross_attention.";
+        std::vector<float> wq(T(ap + "to_q.weight", (int64_t)Hd * C), T(ap + "to_q.weight", (int64_t)Hd * C) + (size_t)Hd * C), bq(Hd, 0.f);
+        fold_affine(wq, bq, Hd, C, T(ap + "norm.weight", C), T(ap + "norm.bias", C));
+        const float* d_wq = upload(wq); const float* d_bq = upload(bq);
+        std::vector<float> wkv(T(ap + "to_kv.weight", (int64_t)2 * Hd * F), T(ap + "to_kv.weight", (int64_t)2 * Hd * F) + (size_t)2 * Hd * F), bkv(2 * Hd, 0.f);
+        fold_affine(wkv, bkv, 2 * Hd, F, T(ap + "norm_context.weight", F), T(ap + "norm_context.bias", F));
+        CrossLayer cl{};
+        cl.wkv = upload(wkv); cl.bkv = upload(bkv);
+        cl.kv_cond = dalloc((size_t)pl.Bmax * pl.cfg.ctx_max_length * 2 * Hd);
+        cl.kv_null = dalloc((size_t)pl.cfg.ctx_max_length * 2 * Hd);
+        const int layer = (int)pl.cross.size();
+        pl.cross.push_back(cl);
+        row_stats(prog, t, C, L, pl.row_stats);
+        ALoad a = make_aload(ts, L, L, 1, 1, 0);
+        a.stats = pl.row_stats; a.stats_mode = 1;
+        emit(prog, gemm_op(a, d_wq, tc_copy(d_wq, wq.size()), d_bq, Hd, 0, nullptr, pl.qc, L));
+        Op at; at.type = OP_ATTN; at.cross = true; at.cross_layer = layer;
+        at.at.q = pl.qc; at.at.ldq = Hd; at.at.k = cl.kv_cond; at.at.v = cl.kv_cond + Hd; at.at.ldkv = 2 * Hd;
+        at.at.k_null = cl.kv_null; at.at.v_null = cl.kv_null + Hd;
+        at.at.o = pl.att; at.at.ldo = Hd; at.at.nq = L; at.at.heads = heads; at.at.d = d;
+        at.at.scale = 1.0f / sqrtf((float)d);
+        emit(prog, at);
+        const float* d_wo = upload(T(ap + "attention.to_out.weight", (int64_t)C * Hd), (size_t)C * Hd);
+        const float* d_bo = upload(T(ap + "attention.to_out.bias", C), C);
+        Src as{pl.att, Hd, nullptr, 0, 1.f};
+        emit(prog, gemm_op(make_aload(as, L, L, 1, 1, 0), d_wo, tc_copy(d_wo, (size_t)C * Hd), d_bo, C, 0, t, t, L));
+      }
+      // ---- feed forward (no norm): Linear -> GELU -> Linear, + residual
+      {
+        const int mid = C * pl.cfg.ff_multiplier;
+        const float* d_w0 = upload(T(bp + "feed_forward.0.weight", (int64_t)mid * C), (size_t)mid * C);
+        const float* d_b0 = upload(T(bp + "feed_forward.0.bias", mid), mid);
+        const float* d_w2 = upload(T(bp + "feed_forward.2.weight", (int64_t)C * mid), (size_t)C * mid);
+        const float* d_b2 = upload(T(bp + "feed_forward.2.bias", C), C);
+        emit(prog, gemm_op(make_aload(ts, L, L, 1, 1, 0), d_w0, tc_copy(d_w0, (size_t)mid * C), d_b0, mid, 1, nullptr, pl.ff, L));
+        Src fs{pl.ff, mid, nullptr, 0, 1.f};
+        emit(prog, gemm_op(make_aload(fs, L, L, 1, 1, 0), d_w2, tc_copy(d_w2, (size_t)C * mid), d_b2, C, 0, t, t, L));
+      }
+    }
+    const float* d_wo = upload(T(pre + "to_out.1.weight", (int64_t)C * C), (size_t)C * C);
+    const float* d_bo = upload(T(pre + "to_out.1.bias", C), C);
+    float* out = acquire();
+    emit(prog, gemm_op(make_aload(ts, L, L, 1, 1, 0), d_wo, tc_copy(d_wo, (size_t)C * C), d_bo, C, 0, nullptr, out, L));
+    release(t);
+    return out;
+  }
+
+  void build() {
+    const mdt_config& c = pl.cfg;
+    std::vector<Op>& prog = pl.unet;
+    const int nlev = c.num_levels, p = c.patch_size;
+    if (c.length % p) raise(MDT_ERR_INVALID, "length %d not divisible by patch_size %d", c.length, p);
+    std::vector<int> Cl(nlev + 1), Ll(nlev + 1);
+    Cl[0] = c.channels * c.multipliers[0]; Ll[0] = c.length / p;
+    for (int i = 0; i < nlev; ++i) {
+      if (Ll[i] % c.factors[i]) raise(MDT_ERR_INVALID, "level %d length %d not divisible by factor %d", i, Ll[i], c.factors[i]);
+      if (c.factors[i] % 2) raise(MDT_ERR_INVALID, "odd resampling factor %d is not supported", c.factors[i]);
+      Cl[i + 1] = c.channels * c.multipliers[i + 1]; Ll[i + 1] = Ll[i] / c.factors[i];
+    }
+    const int Cin0 = Cl[0] / p;  // channels of the to_in / to_out resnets (before patching)
+
+    // ---- workspace sizing (floats per row-sample)
+    size_t S = (size_t)c.length * std::max(Cin0, std::max(c.in_channels, c.out_channels));
+    size_t Sqkv = 4, Satt = 4, Sff = 4, Sup = 4; int Lmax = c.length;
+    for (int i = 0; i <= nlev; ++i) {
+      S = std::max(S, (size_t)Ll[i] * Cl[i] * (i > 0 ? 1 : 1));
+      if (i > 0) {
+        Sqkv = std::max(Sqkv, (size_t)Ll[i] * 3 * pl.Hd);
+        Satt = std::max(Satt, (size_t)Ll[i] * pl.Hd);
+        Sff = std::max(Sff, (size_t)Ll[i] * Cl[i] * c.ff_multiplier);
+        Sup = std::max(Sup, (size_t)Ll[i] * 2 * c.factors[i - 1] * Cl[i - 1]);
+      }
+    }
+    pl.S_act = S;
+    const size_t Be = pl.Beff_max;
+    pl.qkv = dalloc(Sqkv * Be); pl.att = dalloc(Satt * Be); pl.qc = dalloc(Satt * Be); pl.ff = dalloc(Sff * Be);
+    pl.upy = dalloc(Sup * Be);
+    pl.gn_stats = dalloc((size_t)2 * 64 * Be);
+    pl.row_stats = dalloc((size_t)2 * Lmax * Be);
+    pl.xin = dalloc((size_t)c.length * c.in_channels * Be);
+    pl.net_out = dalloc((size_t)c.length * c.out_channels * Be);
+    pl.x = dalloc((size_t)c.length * c.in_channels * pl.Bmax);
+    pl.xmid = dalloc((size_t)c.length * c.in_channels * pl.Bmax);
+    pl.emb = dalloc((size_t)pl.Bmax * c.ctx_max_length * pl.F);
+    pl.emb_stats = dalloc((size_t)pl.Bmax * c.ctx_max_length * 2);
+    pl.emb_null_stats = dalloc((size_t)c.ctx_max_length * 2);
+    if (c.resnet_groups > 32) raise(MDT_ERR_INVALID, "resnet_groups > 32 unsupported");
+
+    // ---- conditioning encoder + time path weights
+    pl.w_fc1 = upload(T("fc1.weight", c.text_embed_dim), c.text_embed_dim);
+    pl.b_fc1 = upload(T("fc1.bias", c.text_embed_dim), c.text_embed_dim);
+    if (c.pos_emb_fourier) {
+      const int half = (c.embed_dim_position + 1) / 2;
+      pl.inv_freq = upload(T("p_enc_1d.inv_freq", half), half);
+      if (c.embed_dim_position % 2) raise(MDT_ERR_INVALID, "odd embed_dim_position unsupported");
+      if (c.pos_emb_fourier_add && c.embed_dim_position != c.text_embed_dim)
+        raise(MDT_ERR_INVALID, "pos_emb_fourier_add needs embed_dim_position == text_embed_dim");
+      if (!c.pos_emb_fourier_add && c.embed_dim_position > c.text_embed_dim)
+        raise(MDT_ERR_INVALID, "embed_dim_position > text_embed_dim truncates the encoding (transformer.py:3470)");
+    }
+    const int expectF = c.text_embed_dim + ((c.pos_emb_fourier && !c.pos_emb_fourier_add) ? c.embed_dim_position : 0);
+    if (expectF != pl.F) raise(MDT_ERR_INVALID, "ctx_features %d != encoder width %d", pl.F, expectF);
+    pl.w_null_emb = upload(T("unet.fixed_embedding.embedding.weight", (int64_t)c.ctx_max_length * pl.F),
+                           (size_t)c.ctx_max_length * pl.F);
+    const int Mf = c.mapping_features, half = c.channels / 2;
+    pl.w_time_freq = upload(T("unet.to_time.0.0.weights", half), half);
+    pl.w_time = upload(T("unet.to_time.0.1.weight", (int64_t)Mf * (c.channels + 1)), (size_t)Mf * (c.channels + 1));
+    pl.b_time = upload(T("unet.to_time.0.1.bias", Mf), Mf);
+    pl.w_map0 = upload(T("unet.to_mapping.0.weight", (int64_t)Mf * Mf), (size_t)Mf * Mf);
+    pl.b_map0 = upload(T("unet.to_mapping.0.bias", Mf), Mf);
+    pl.w_map2 = upload(T("unet.to_mapping.2.weight", (int64_t)Mf * Mf), (size_t)Mf * Mf);
+    pl.b_map2 = upload(T("unet.to_mapping.2.bias", Mf), Mf);
+    pl.t_calls = dalloc(pl.max_calls);
+    pl.t_feat = dalloc((size_t)pl.max_calls * (c.channels + 1));
+    pl.t_a = dalloc((size_t)pl.max_calls * Mf);
+    pl.t_b = dalloc((size_t)pl.max_calls * Mf);
+    pl.t_map = dalloc((size_t)pl.max_calls * Mf);
+
+    // ---- UNet program (UNet1d.forward, modules.py:1144-1180)
+    const std::string U = "unet.";
+    Src xin{pl.xin, c.in_channels, nullptr, 0, 1.f};
+    float* cur = resnet(prog, U + "to_in.block.", xin, c.length, Cin0, 1);
+    if (p > 1) {
+      float* pt = acquire();
+      Op op; op.type = OP_PERMUTE; op.in0 = cur; op.out = pt; op.i0 = Ll[0]; op.i1 = Cin0; op.i2 = p; op.i3 = 1;
+      emit(prog, op);
+      release(cur); cur = pt;
+    }
+    set_tap(prog, "to_in", cur, Ll[0], Cl[0]);
+    const float* skip0 = cur;  // held until the end
+    std::vector<std::vector<const float*>> skips(nlev);
+    const float* xcur = cur;
+    bool xcur_owned = false;   // skip0 must not be released
+    for (int i = 0; i < nlev; ++i) {
+      const std::string dp = U + "downsamples." + std::to_string(i) + ".";
+      const int f = c.factors[i], k = f * c.kernel_multiplier_downsample + 1, pad = f * (c.kernel_multiplier_downsample / 2);
+      const int Ci = Cl[i], Co = Cl[i + 1], Lo = Ll[i + 1];
+      auto wd = pack_conv(T(dp + "downsample.weight", (int64_t)Co * Ci * k), Co, Ci, k);
+      const float* d_wd = upload(wd);
+      const float* d_bd = upload(T(dp + "downsample.bias", Co), Co);
+      float* y = acquire();
+      Src xs{xcur, Ci, nullptr, 0, 1.f};
+      emit(prog, gemm_op(make_aload(xs, Ll[i], Lo, k, f, pad), d_wd, tc_copy(d_wd, wd.size()), d_bd, Co, 0, nullptr, y, Lo));
+      set_tap(prog, "down" + std::to_string(i) + ".downsample", y, Lo, Co);
+      if (xcur_owned) release(xcur);
+      xcur = y; xcur_owned = true;
+      if (has(dp + "pre_transformer_block.to_in.0.weight")) {
+        float* t = transformer(prog, dp + "pre_transformer_block.", xcur, Lo, Co, false);
+        set_tap(prog, "down" + std::to_string(i) + ".pre", t, Lo, Co);
+        release(xcur); xcur = t;  // the pre-transformer skip is never consumed: not stored
+      }
+      for (int j = 0; j < c.num_blocks[i]; ++j) {
+        Src s{xcur, Co, nullptr, 0, 1.f};
+        float* r = resnet(prog, dp + "blocks." + std::to_string(j) + ".", s, Lo, Co, c.resnet_groups);
+        set_tap(prog, "down" + std::to_string(i) + ".res" + std::to_string(j), r, Lo, Co);
+        // previous xcur: release unless it is a stored skip
+        if (j == 0) release(xcur);
+        skips[i].push_back(r);
+        xcur = r;
+      }
+      if (c.attentions[i] > 0) {
+        float* t = transformer(prog, dp + "transformer.", xcur, Lo, Co, true);
+        set_tap(prog, "down" + std::to_string(i) + ".tr", t, Lo, Co);
+        skips[i].push_back(t);
+        xcur = t;
+      }
+      xcur_owned = false;  // xcur is a stored skip now
+      if (c.num_blocks[i] == 0 && c.attentions[i] == 0) raise(MDT_ERR_INVALID, "level without blocks unsupported");
+    }
+    {
+      const std::string bp = U + "bottleneck.";
+      const int Cb = Cl[nlev], Lb = Ll[nlev];
+      Src s{xcur, Cb, nullptr, 0, 1.f};
+      float* r = resnet(prog, bp + "pre_block.", s, Lb, Cb, c.resnet_groups);
+      set_tap(prog, "mid.pre", r, Lb, Cb);
+      xcur = r;
+      if (c.attentions[nlev] > 0 && has(bp + "transformer.to_in.0.weight")) {
+        float* t = transformer(prog, bp + "transformer.", xcur, Lb, Cb, true);
+        set_tap(prog, "mid.tr", t, Lb, Cb);
+        release(xcur); xcur = t;
+      }
+      Src s2{xcur, Cb, nullptr, 0, 1.f};
+      float* r2 = resnet(prog, bp + "post_block.", s2, Lb, Cb, c.resnet_groups);
+      set_tap(prog, "mid.post", r2, Lb, Cb);
+      release(xcur); xcur = r2;
+    }
+    const float skip_scale = c.use_skip_scale ? (float)pow(2.0, -0.5) : 1.0f;
+    for (int u = 0; u < nlev; ++u) {
+      const int i = nlev - 1 - u;
+      const std::string up = U + "upsamples." + std::to_string(u) + ".";
+      const int Ci = Cl[i + 1], Co = Cl[i], Li = Ll[i + 1], f = c.factors[i];
+      const int nres = c.num_blocks[i] + (c.attentions[i] ? 1 : 0);
+      if ((int)skips[i].size() != nres) raise(MDT_ERR_INVALID, "skip bookkeeping mismatch at level %d", i);
+      for (int j = 0; j < nres; ++j) {
+        const float* sk = skips[i].back(); skips[i].pop_back();
+        Src s{xcur, Ci, sk, Ci, skip_scale};
+        float* r = resnet(prog, up + "blocks." + std::to_string(j) + ".", s, Li, Ci, c.resnet_groups);
+        set_tap(prog, "up" + std::to_string(u) + ".res" + std::to_string(j), r, Li, Ci);
+        release(xcur); release(sk);
+        xcur = r;
+      }
+      if (has(up + "pre_transformer_block.to_in.0.weight")) {
+        float* t = transformer(prog, up + "pre_transformer_block.", xcur, Li, Ci, false);
+        set_tap(prog, "up" + std::to_string(u) + ".pre", t, Li, Ci);
+        release(xcur); xcur = t;
+      }
+      if (c.attentions[i] > 0) {
+        float* t = transformer(prog, up + "transformer.", xcur, Li, Ci, true);
+        set_tap(prog, "up" + std::to_string(u) + ".tr", t, Li, Ci);
+        release(xcur); xcur = t;
+      }
+      // ConvTranspose1d(Ci -> Co, k = 2f, stride f, pad f/2): GEMM to [Li][2f*Co] then two-tap gather
+      const int K2 = 2 * f;
+      const float* wt = T(up + "upsample.weight", (int64_t)Ci * Co * K2);
+      std::vector<float> wp((size_t)K2 * Co * Ci);
+      for (int ci = 0; ci < Ci; ++ci)
+        for (int co = 0; co < Co; ++co)
+          for (int kk = 0; kk < K2; ++kk) wp[((size_t)kk * Co + co) * Ci + ci] = wt[((size_t)ci * Co + co) * K2 + kk];
+      const float* d_wp = upload(wp);
+      const float* d_bu = upload(T(up + "upsample.bias", Co), Co);
+      Src s{xcur, Ci, nullptr, 0, 1.f};
+      emit(prog, gemm_op(make_aload(s, Li, Li, 1, 1, 0), d_wp, tc_copy(d_wp, wp.size()), nullptr, K2 * Co, 0, nullptr, pl.upy, Li));
+      float* y = acquire();
+      Op op; op.type = OP_UPGATHER; op.in0 = pl.upy; op.in1 = d_bu; op.in2 = (i == 0) ? skip0 : nullptr; op.out = y;
+      op.i0 = Li; op.i1 = Co; op.i2 = f;
+      emit(prog, op);
+      set_tap(prog, "up" + std::to_string(u) + ".upsample", y, Li * f, Co);
+      release(xcur); xcur = y;
+    }
+    release(skip0);
+    if (p > 1) {
+      float* pt = acquire();
+      Op op; op.type = OP_PERMUTE; op.in0 = xcur; op.out = pt; op.i0 = Ll[0]; op.i1 = Cin0; op.i2 = p; op.i3 = 0;
+      emit(prog, op);
+      release(xcur); xcur = pt;
+    }
+    {
+      Src s{xcur, Cin0, nullptr, 0, 1.f};
+      float* r = resnet(prog, U + "to_out.block.", s, c.length, c.out_channels, 1);
+      // the program must end in pl.net_out: retarget the last GEMM(s) of the block
+      for (auto it = prog.rbegin(); it != prog.rend(); ++it) {
+        if (it->type == OP_GEMM && it->g.C == r) { it->g.C = pl.net_out; if (it->g.res == r) it->g.res = pl.net_out; }
+        else if (it->type == OP_GEMM) break;
+        else if (it->type != OP_GN_STATS) break;
+      }
+      set_tap(prog, "to_out", pl.net_out, c.length, c.out_channels);
+      release(xcur); release(r);
+    }
+    CK(cudaDeviceSynchronize());
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// execution
+// ------------------------------------------------------------------------------------------------
+static void launch_gemm(mdt_plan& pl, const GemmParams& g, cudaStream_t s) {
+  if (g.M <= 0) return;
+  if (pl.prec != MDT_PREC_FP32 && g.Wtc && gemm_tc_supported(g)) CK(launch_gemm_tc(g, pl.prec, s));
+  else CK(launch_gemm_fp32(g, s));
+  pl.launches++;
+}
+
+static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_cond, int n_ctx, cudaStream_t s) {
+  for (Op& op : prog) {
+    switch (op.type) {
+      case OP_GEMM: { GemmParams g = op.g; g.M = Beff * op.rps; launch_gemm(pl, g, s); break; }
+      case OP_GN_STATS: { NormStatsParams n = op.ns; n.rows = Beff; CK(launch_groupnorm_stats(n, s)); pl.launches++; break; }
+      case OP_ROW_STATS: { NormStatsParams n = op.ns; n.rows = Beff * op.rps; CK(launch_rownorm_stats(n, s)); pl.launches++; break; }
+      case OP_ATTN: {
+        AttnParams a = op.at; a.B = Beff;
+        if (op.cross) { a.nk = n_ctx; a.kv_sample_stride = (long long)n_ctx * a.ldkv; a.n_cond = n_cond; }
+        CK(launch_attention(a, s)); pl.launches++; break;
+      }
+      case OP_UPGATHER: CK(launch_upsample_gather(op.in0, op.in1, op.in2, op.out, Beff, op.i0, op.i1, op.i2, s)); pl.launches++; break;
+      case OP_PERMUTE: CK(launch_patch_permute(op.in0, op.out, Beff, op.i0, op.i1, op.i2, op.i3, s)); pl.launches++; break;
+    }
+    if (pl.taps_on && !op.tap.empty()) {
+      CK(cudaStreamSynchronize(s));
+      std::vector<float>& dst = pl.tap_store[op.tap];
+      dst.resize((size_t)Beff * op.tap_rps * op.tap_c);
+      CK(cudaMemcpy(dst.data(), op.tap_ptr, dst.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+  }
+}
+
+static GemmParams dense(const float* A, int K, const float* W, const float* b, int N, int M, int act, float* C, bool silu_in) {
+  GemmParams g{};
+  g.a.src0 = A; g.a.src1 = nullptr; g.a.c0 = K; g.a.c1 = 0; g.a.C = K; g.a.scale1 = 1.f;
+  g.a.L_in = 1; g.a.L_out = 1; g.a.taps = 1; g.a.stride = 1; g.a.pad = 0; g.a.stats = nullptr; g.a.stats_mode = 0;
+  g.a.groups = 1; g.a.cpg = K; g.a.aff = nullptr; g.a.aff_call_stride = 0; g.a.call_idx = nullptr; g.a.silu = silu_in ? 1 : 0;
+  g.W = W; g.Wtc = nullptr; g.bias = b; g.M = M; g.N = N; g.K = K; g.act = act; g.res = nullptr; g.ldres = N; g.C = C; g.ldc = N;
+  return g;
+}
+
+// time -> mapping -> per-resnet FiLM tables for `rows` denoiser calls (UNet1d.get_mapping, modules.py:1123-1142;
+// MappingToScaleShift, modules.py:138-142).  Always fp32: it is sigma-only, batch-invariant work.
+static void run_time_tables(mdt_plan& pl, int rows, cudaStream_t s) {
+  const mdt_config& c = pl.cfg;
+  const int Mf = c.mapping_features;
+  CK(launch_time_features(pl.t_calls, pl.w_time_freq, pl.t_feat, rows, c.channels / 2, s)); pl.launches++;
+  CK(launch_gemm_fp32(dense(pl.t_feat, c.channels + 1, pl.w_time, pl.b_time, Mf, rows, 1, pl.t_a, false), s));
+  CK(launch_gemm_fp32(dense(pl.t_a, Mf, pl.w_map0, pl.b_map0, Mf, rows, 1, pl.t_b, false), s));
+  CK(launch_gemm_fp32(dense(pl.t_b, Mf, pl.w_map2, pl.b_map2, Mf, rows, 1, pl.t_map, false), s));
+  pl.launches += 3;
+  for (Film& f : pl.films) {
+    CK(launch_gemm_fp32(dense(pl.t_map, Mf, f.w_ss, f.b_ss, 2 * f.C, rows, 0, f.ss, true), s));
+    CK(launch_film_fold(f.ss, f.gamma, f.beta, f.aff, rows, f.C, s));
+    pl.launches += 2;
+  }
+}
+
+// conditioning embedding -> per-layer cross-attention K/V (loop invariant)
+static void run_context(mdt_plan& pl, const float* cond_dev, int Bc, int n_ctx, bool cfg, cudaStream_t s) {
+  const mdt_config& c = pl.cfg;
+  const int F = pl.F, Hd = pl.Hd;
+  CK(launch_encode_cond(cond_dev, pl.w_fc1, pl.b_fc1, pl.inv_freq, pl.emb, Bc, n_ctx, c.text_embed_dim,
+                        c.pos_emb_fourier ? c.embed_dim_position : 0, c.pos_emb_fourier_add, s));
+  NormStatsParams n{}; n.src0 = pl.emb; n.c0 = F; n.scale1 = 1.f; n.L = 1; n.groups = 1; n.eps = 1e-5f; n.stats = pl.emb_stats; n.rows = Bc * n_ctx;
+  CK(launch_rownorm_stats(n, s));
+  pl.launches += 2;
+  if (cfg) {
+    n.src0 = pl.w_null_emb; n.stats = pl.emb_null_stats; n.rows = n_ctx;
+    CK(launch_rownorm_stats(n, s)); pl.launches++;
+  }
+  for (CrossLayer& cl : pl.cross) {
+    GemmParams g = dense(pl.emb, F, cl.wkv, cl.bkv, 2 * Hd, Bc * n_ctx, 0, cl.kv_cond, false);
+    g.a.stats = pl.emb_stats; g.a.stats_mode = 1;
+    CK(launch_gemm_fp32(g, s)); pl.launches++;
+    if (cfg) {
+      GemmParams gn = dense(pl.w_null_emb, F, cl.wkv, cl.bkv, 2 * Hd, n_ctx, 0, cl.kv_null, false);
+      gn.a.stats = pl.emb_null_stats; gn.a.stats_mode = 1;
+      CK(launch_gemm_fp32(gn, s)); pl.launches++;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* mdt_last_error(void) { return g_err; }
+int mdt_abi_version(void) { return MDT_ABI_VERSION; }
+
+int mdt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+  }
+  return ok;
+}
+
+int mdt_karras_sigmas(int num_steps, double sigma_min, double sigma_max, double rho, float* out) {
+  if (num_steps < 2 || !out) return fail(MDT_ERR_INVALID, "num_steps must be >= 2");
+  const double rho_inv = 1.0 / rho;
+  const float a = (float)pow(sigma_max, rho_inv);
+  const float d = (float)(pow(sigma_min, rho_inv) - pow(sigma_max, rho_inv));
+  for (int i = 0; i < num_steps; ++i) {
+    const float frac = (float)i / (float)(num_steps - 1);
+    const float base = a + frac * d;
+    out[i] = powf(base, (float)rho);
+  }
+  out[num_steps] = 0.f;
+  return 0;
+}
+
+static void scale_weights(float s, double sigma_data, float* c_in, float* c_noise, float* c_skip, float* c_out) {
+  const float sd2 = (float)(sigma_data * sigma_data);
+  const float s2 = s * s;
+  *c_noise = logf(s) * 0.25f;
+  *c_skip = sd2 / (s2 + sd2);
+  *c_out = (s * (float)sigma_data) * (1.0f / sqrtf(sd2 + s2));
+  *c_in = 1.0f / sqrtf(s2 + sd2);
+}
+
+int mdt_adpm2_scalars(const float* sigmas, int n_iters, double rho, double sigma_data, mdt_iter_scalars* out) {
+  if (!sigmas || !out || n_iters < 0) return fail(MDT_ERR_INVALID, "bad arguments");
+  for (int i = 0; i < n_iters; ++i) {
+    const float s = sigmas[i], sn = sigmas[i + 1];
+    const float sn2 = sn * sn, s2 = s * s;
+    const float q = sn2 * (s2 - sn2) / s2;
+    const double up = sqrt((double)q);
+    const float dn_in = sn2 - (float)(up * up);
+    const double down = sqrt((double)dn_in);
+    float mid;
+    if (rho == 1.0) mid = (s + (float)down) / 2.0f;
+    else mid = powf((powf(s, (float)(1.0 / rho)) + (float)pow(down, 1.0 / rho)) / 2.0f, (float)rho);
+    mdt_iter_scalars& o = out[i];
+    o.sigma = s; o.sigma_mid = mid;
+    scale_weights(s, sigma_data, &o.c_in_a, &o.c_noise_a, &o.c_skip_a, &o.c_out_a);
+    scale_weights(mid, sigma_data, &o.c_in_b, &o.c_noise_b, &o.c_skip_b, &o.c_out_b);
+    o.dt_mid = mid - s;
+    o.dt_down = (float)down - s;
+    o.sigma_up = (float)up;
+  }
+  return 0;
+}
+
+int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_tensors, int device, mdt_plan** out) {
+  if (!cfg || !tensors || !out) return fail(MDT_ERR_INVALID, "null argument");
+  if (cfg->abi_version != MDT_ABI_VERSION) return fail(MDT_ERR_INVALID, "ABI version mismatch (%d != %d)", cfg->abi_version, MDT_ABI_VERSION);
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(MDT_ERR_NO_DEVICE, "no CUDA device visible: this library has no CPU fallback"); }
+  if (device < 0 || device >= ndev) return fail(MDT_ERR_INVALID, "device %d out of range", device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(MDT_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(MDT_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  if (cfg->num_levels < 1 || cfg->num_levels > MDT_MAX_LEVELS) return fail(MDT_ERR_INVALID, "num_levels out of range");
+  if (cfg->max_batch < 1) return fail(MDT_ERR_INVALID, "max_batch must be >= 1");
+  if (cfg->precision < 0 || cfg->precision > 2) return fail(MDT_ERR_INVALID, "unknown precision %d", cfg->precision);
+  mdt_plan* pl = new mdt_plan();
+  try {
+    CK(cudaSetDevice(device));
+    CK(init_kernels());
+    CK(init_gemm_tc());
+    pl->cfg = *cfg; pl->device = device; pl->prec = cfg->precision;
+    pl->P = cfg->in_channels; pl->L0 = cfg->length; pl->Hd = cfg->heads * cfg->head_features; pl->F = cfg->ctx_features;
+    pl->Bmax = cfg->max_batch; pl->Beff_max = 2 * cfg->max_batch;
+    const int max_steps = cfg->max_timesteps > 1 ? cfg->max_timesteps : 256;
+    pl->max_calls = 2 * (max_steps - 1);
+    const char* eg = getenv("MDT_GRAPH");
+    pl->use_graph = !(eg && eg[0] == '0');
+    size_t total = 0;
+    for (int64_t i = 0; i < n_tensors; ++i) {
+      if (!tensors[i].name || !tensors[i].data) raise(MDT_ERR_INVALID, "tensor %lld has a null field", (long long)i);
+      pl->tensors[tensors[i].name] = {tensors[i].data, tensors[i].numel};
+      total += (size_t)tensors[i].numel;
+    }
+    pl->wcap = total * sizeof(float) * (pl->prec == MDT_PREC_FP32 ? 2 : 3) + (64u << 20);
+    { void* p = nullptr; cudaError_t e = cudaMalloc(&p, pl->wcap); if (e != cudaSuccess) raise(MDT_ERR_OOM, "weight slab cudaMalloc(%zu) failed: %s", pl->wcap, cudaGetErrorString(e)); pl->wslab = (char*)p; }
+    CK(cudaMalloc((void**)&pl->d_iters, sizeof(IterScalars) * (pl->max_calls / 2 + 1)));
+    CK(cudaMallocHost((void**)&pl->h_iters, sizeof(IterScalars) * (pl->max_calls / 2 + 1)));
+    CK(cudaMallocHost((void**)&pl->h_tcalls, sizeof(float) * (pl->max_calls + 2)));
+    CK(cudaMalloc((void**)&pl->d_call, sizeof(int)));
+    CK(cudaMemset(pl->d_call, 0, sizeof(int)));
+    Builder b(*pl);
+    b.build();
+    pl->tensors.clear();  // host pointers are not retained past creation
+  } catch (const MdtError& e) {
+    int code = e.code;
+    snprintf(g_err, sizeof(g_err), "%s", e.msg.c_str());
+    mdt_plan_destroy(pl);
+    return code;
+  }
+  *out = pl;
+  return 0;
+}
+
+void mdt_plan_destroy(mdt_plan* pl) {
+  if (!pl) return;
+  cudaSetDevice(pl->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : pl->graphs) cudaGraphExecDestroy(kv.second.exec);
+  for (void* p : pl->allocs) cudaFree(p);
+  if (pl->wslab) cudaFree(pl->wslab);
+  if (pl->d_iters) cudaFree(pl->d_iters);
+  if (pl->h_iters) cudaFreeHost(pl->h_iters);
+  if (pl->h_tcalls) cudaFreeHost(pl->h_tcalls);
+  if (pl->d_call) cudaFree(pl->d_call);
+  cudaGetLastError();
+  delete pl;
+}
+
+int64_t mdt_plan_device_bytes(const mdt_plan* pl) { return pl ? (int64_t)(pl->wcap + pl->act_bytes) : 0; }
+int64_t mdt_plan_launch_count(const mdt_plan* pl) { return pl ? pl->launches : 0; }
+
+int mdt_plan_enable_taps(mdt_plan* pl, int enable) {
+  if (!pl) return fail(MDT_ERR_INVALID, "null plan");
+  pl->taps_on = enable != 0;
+  pl->tap_store.clear();
+  return 0;
+}
+
+int64_t mdt_plan_read_tap(mdt_plan* pl, const char* name, float* host_dst, int64_t capacity) {
+  if (!pl || !name) return fail(MDT_ERR_INVALID, "null argument");
+  auto it = pl->tap_store.find(name);
+  if (it == pl->tap_store.end()) return fail(MDT_ERR_INVALID, "tap '%s' not recorded", name);
+  const int64_t n = (int64_t)it->second.size();
+  if (host_dst) {
+    if (capacity < n) return fail(MDT_ERR_INVALID, "tap '%s' needs %lld floats", name, (long long)n);
+    memcpy(host_dst, it->second.data(), n * sizeof(float));
+  }
+  return n;
+}
+
+static int check_ctx(mdt_plan* pl, int n_ctx) {
+  if (n_ctx < 1 || n_ctx > pl->cfg.ctx_max_length)
+    return fail(MDT_ERR_INVALID, "Input sequence length must be <= max_length (%d > %d)", n_ctx, pl->cfg.ctx_max_length);
+  return 0;
+}
+
+int mdt_plan_unet_forward(mdt_plan* pl, const float* x_dev, float time, const float* cond_dev, int32_t n_ctx,
+                          int64_t B, float cond_scale, float* out_dev, void* stream) {
+  if (!pl || !x_dev || !cond_dev || !out_dev) return fail(MDT_ERR_INVALID, "null argument");
+  if (B < 1 || B > pl->Bmax) return fail(MDT_ERR_INVALID, "B=%lld exceeds plan max_batch=%d", (long long)B, pl->Bmax);
+  if (check_ctx(pl, n_ctx)) return MDT_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  try {
+    CK(cudaSetDevice(pl->device));
+    const bool cfg = cond_scale != 1.0f;
+    const int Bc = (int)B, Beff = cfg ? 2 * Bc : Bc;
+    CK(cudaStreamSynchronize(s));
+    pl->h_tcalls[0] = time;
+    CK(cudaMemcpyAsync(pl->t_calls, pl->h_tcalls, sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(launch_set_int(pl->d_call, 0, s));
+    run_time_tables(*pl, 1, s);
+    run_context(*pl, cond_dev, Bc, n_ctx, cfg, s);
+    CK(launch_to_token_major(x_dev, pl->xin, Bc, pl->P, pl->L0, 1.0f, cfg ? 1 : 0, s));
+    run_program(*pl, pl->unet, Beff, Bc, n_ctx, s);
+    CK(launch_cfg_mix_to_bpl(pl->net_out, out_dev, Bc, pl->cfg.out_channels, pl->L0, cond_scale, cfg ? 1 : 0, s));
+    pl->launches += 3;
+  } catch (const MdtError& e) {
+    snprintf(g_err, sizeof(g_err), "%s", e.msg.c_str());
+    return e.code;
+  }
+  return 0;
+}
+
+static void run_iteration(mdt_plan& pl, StepParams& sp, int Beff, int Bc, int n_ctx, cudaStream_t s) {
+  run_program(pl, pl.unet, Beff, Bc, n_ctx, s);
+  CK(launch_step_update(0, sp, s));
+  CK(launch_add_int(pl.d_call, 1, s));
+  run_program(pl, pl.unet, Beff, Bc, n_ctx, s);
+  CK(launch_step_update(1, sp, s));
+  CK(launch_add_int(pl.d_call, 1, s));
+  pl.launches += 4;
+}
+
+int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const float* noise0_dev,
+                    const float* step_noise_dev, const mdt_iter_scalars* iters, int32_t n_iters, uint64_t seed,
+                    uint64_t sample_offset, int64_t B, float cond_scale, int32_t clamp, float* out_dev,
+                    uint8_t* tokens_dev, void* stream) {
+  if (!pl || !cond_dev || !iters) return fail(MDT_ERR_INVALID, "null argument");
+  if (!out_dev && !tokens_dev) return fail(MDT_ERR_INVALID, "one of out_dev / tokens_dev is required");
+  if (B < 0) return fail(MDT_ERR_INVALID, "negative batch");
+  if (n_iters < 1) return fail(MDT_ERR_INVALID, "timesteps must be >= 2");
+  if (2 * n_iters > pl->max_calls) return fail(MDT_ERR_INVALID, "timesteps %d exceeds the plan's max_timesteps %d", n_iters + 1, pl->max_calls / 2 + 1);
+  if (check_ctx(pl, n_ctx)) return MDT_ERR_INVALID;
+  if (tokens_dev && pl->cfg.out_channels > 256) return fail(MDT_ERR_INVALID, "uint8 tokens need pred_dim <= 256");
+  if (pl->cfg.in_channels != pl->cfg.out_channels) return fail(MDT_ERR_INVALID, "sampler needs in_channels == out_channels");
+  if (B == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  static_assert(sizeof(IterScalars) == sizeof(mdt_iter_scalars), "scalar layout mismatch");
+  try {
+    CK(cudaSetDevice(pl->device));
+    const bool cfg = cond_scale != 1.0f;
+    const int P = pl->P, L = pl->L0;
+    const size_t per = (size_t)P * L;
+    // a previous call's async copies out of the pinned staging buffers must have drained
+    CK(cudaStreamSynchronize(s));
+    memcpy(pl->h_iters, iters, sizeof(IterScalars) * n_iters);
+    for (int i = 0; i < n_iters; ++i) { pl->h_tcalls[2 * i] = iters[i].c_noise_a; pl->h_tcalls[2 * i + 1] = iters[i].c_noise_b; }
+    CK(cudaMemcpyAsync(pl->d_iters, pl->h_iters, sizeof(IterScalars) * n_iters, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(pl->t_calls, pl->h_tcalls, sizeof(float) * 2 * n_iters, cudaMemcpyHostToDevice, s));
+    run_time_tables(*pl, 2 * n_iters, s);
+    for (int64_t b0 = 0; b0 < B; b0 += pl->Bmax) {
+      const int Bc = (int)std::min<int64_t>(pl->Bmax, B - b0);
+      const int Beff = cfg ? 2 * Bc : Bc;
+      run_context(*pl, cond_dev + (size_t)b0 * n_ctx, Bc, n_ctx, cfg, s);
+      CK(launch_step_init(noise0_dev ? noise0_dev + (size_t)b0 * per : nullptr, pl->x, pl->xin, pl->d_iters, seed,
+                          sample_offset + (uint64_t)b0, Bc, P, L, cfg ? 1 : 0, s));
+      CK(launch_set_int(pl->d_call, 0, s));
+      pl->launches += 2;
+      StepParams sp{};
+      sp.iters = pl->d_iters; sp.call_idx = pl->d_call; sp.net = pl->net_out; sp.x = pl->x; sp.xmid = pl->xmid; sp.xin = pl->xin;
+      sp.noise = step_noise_dev ? step_noise_dev + (size_t)b0 * per : nullptr;
+      sp.noise_iter_stride = (long long)B * (long long)per;
+      sp.seed = seed; sp.sample_offset = sample_offset + (uint64_t)b0; sp.cond_scale = cond_scale; sp.cfg = cfg ? 1 : 0;
+      sp.B = Bc; sp.P = P; sp.L = L; sp.n_iters = n_iters; sp.out = nullptr; sp.tokens = nullptr; sp.clamp = clamp;
+      if (pl->use_graph && !pl->taps_on) {
+        // one captured iteration, replayed n_iters times; all per-iteration data is device resident
+        std::vector<long long> key = {Bc, n_ctx, cfg ? 1 : 0, (long long)(uintptr_t)sp.noise, sp.noise_iter_stride,
+                                      (long long)seed, (long long)sp.sample_offset, (long long)n_iters,
+                                      (long long)(cond_scale * 65536.0)};
+        auto it = pl->graphs.find(key);
+        if (it == pl->graphs.end()) {
+          if (pl->graphs.size() > 16) { for (auto& kv : pl->graphs) cudaGraphExecDestroy(kv.second.exec); pl->graphs.clear(); }
+          cudaStream_t cs;
+          CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+          cudaGraph_t graph = nullptr;
+          const long long before = pl->launches;
+          CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+          try { run_iteration(*pl, sp, Beff, Bc, n_ctx, cs); }
+          catch (...) { cudaStreamEndCapture(cs, &graph); if (graph) cudaGraphDestroy(graph); cudaStreamDestroy(cs); throw; }
+          CK(cudaStreamEndCapture(cs, &graph));
+          pl->launches = before;
+          cudaGraphExec_t exec = nullptr;
+          CK(cudaGraphInstantiate(&exec, graph, 0));
+          CK(cudaGraphDestroy(graph));
+          CK(cudaStreamDestroy(cs));
+          it = pl->graphs.emplace(key, mdt_plan::GraphEntry{exec}).first;
+        }
+        long long per_iter = 0;
+        for (const Op& op : pl->unet) { (void)op; per_iter++; }
+        for (int i = 0; i < n_iters; ++i) CK(cudaGraphLaunch(it->second.exec, s));
+        pl->launches += (long long)n_iters * (2 * per_iter + 4);
+      } else {
+        for (int i = 0; i < n_iters; ++i) run_iteration(*pl, sp, Beff, Bc, n_ctx, s);
+      }
+      CK(launch_finalize(pl->x, out_dev ? out_dev + (size_t)b0 * per : nullptr,
+                         tokens_dev ? tokens_dev + (size_t)b0 * L : nullptr, Bc, P, L, clamp, s));
+      pl->launches++;
+    }
+  } catch (const MdtError& e) {
+    snprintf(g_err, sizeof(g_err), "%s", e.msg.c_str());
+    return e.code;
+  }
+  return 0;
+}
+
+int mdt_op_linear(const float* a_dev, const float* w_dev, const float* bias_dev, const float* res_dev, float* c_dev,
+                  int64_t M, int32_t N, int32_t K, int32_t act, int32_t precision, void* stream) {
+  if (!a_dev || !w_dev || !c_dev) return fail(MDT_ERR_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (init_kernels() != cudaSuccess || init_gemm_tc() != cudaSuccess) return fail(MDT_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+  GemmParams g = dense(a_dev, K, w_dev, bias_dev, N, (int)M, act, c_dev, false);
+  g.res = res_dev;
+  cudaError_t e;
+  if (precision == MDT_PREC_FP32) e = launch_gemm_fp32(g, s);
+  else {
+    if (!gemm_tc_supported(g)) return fail(MDT_ERR_INVALID, "shape M=%lld N=%d K=%d unsupported by the tcgen05 kernel", (long long)M, N, K);
+    void* wtc = nullptr;
+    const size_t n = (size_t)N * K;
+    if (cudaMalloc(&wtc, n * 4) != cudaSuccess) return fail(MDT_ERR_OOM, "cudaMalloc failed");
+    e = convert_weights_tc(w_dev, wtc, (long long)n, precision, s);
+    g.Wtc = wtc;
+    if (e == cudaSuccess) e = launch_gemm_tc(g, precision, s);
+    cudaStreamSynchronize(s);
+    cudaFree(wtc);
+  }
+  if (e != cudaSuccess) return fail(MDT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int mdt_op_step_update(int which, const float* net_dev, float* x_dev, float* xmid_dev, float* xin_dev,
+                       const float* noise_dev, const mdt_iter_scalars* it, float cond_scale, int64_t B, int32_t P,
+                       int32_t L, int cfg, void* stream) {
+  if (!net_dev || !x_dev || !xmid_dev || !xin_dev || !it) return fail(MDT_ERR_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  static IterScalars* d_it = nullptr;
+  static int* d_call = nullptr;
+  if (!d_it) {
+    if (cudaMalloc((void**)&d_it, 2 * sizeof(IterScalars)) != cudaSuccess || cudaMalloc((void**)&d_call, sizeof(int)) != cudaSuccess)
+      return fail(MDT_ERR_OOM, "cudaMalloc failed");
+    cudaMemset(d_call, 0, sizeof(int));
+  }
+  IterScalars two[2];
+  memcpy(&two[0], it, sizeof(IterScalars)); memcpy(&two[1], it, sizeof(IterScalars));
+  cudaMemcpyAsync(d_it, two, sizeof(two), cudaMemcpyHostToDevice, s);
+  cudaStreamSynchronize(s);
+  StepParams sp{};
+  sp.iters = d_it; sp.call_idx = d_call; sp.net = net_dev; sp.x = x_dev; sp.xmid = xmid_dev; sp.xin = xin_dev;
+  sp.noise = noise_dev; sp.noise_iter_stride = 0; sp.seed = 0; sp.sample_offset = 0; sp.cond_scale = cond_scale; sp.cfg = cfg;
+  sp.B = (int)B; sp.P = P; sp.L = L; sp.n_iters = 2; sp.clamp = 0;
+  cudaError_t e = launch_step_update(which, sp, s);
+  if (e != cudaSuccess) return fail(MDT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"
