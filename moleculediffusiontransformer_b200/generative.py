@@ -128,6 +128,9 @@ class _QMBase(nn.Module):
         b = sequences.shape[0]
         if sequences.shape[1] > self.unet.fixed_embedding.max_length:
             raise AssertionError("Input sequence length must be <= max_length")  # modules.py:1194-1195
+        if b == 0:  # nothing to launch; keep the reference's return contract
+            empty = torch.empty((0, self.pred_dim, self.max_length), dtype=torch.float32, device=device)
+            return (empty, torch.empty((0, self.max_length), dtype=torch.uint8, device=device)) if return_tokens else empty
         if noise is None and seed is None:
             noise = torch.randn(b, self.pred_dim, self.max_length)
         if noise is not None:

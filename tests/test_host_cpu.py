@@ -1,0 +1,151 @@
+"""CPU-only checks: C-ABI library loads and exports every declared symbol, host scalar plan, launcher logic."""
+import ctypes
+import math
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from moleculediffusiontransformer_b200 import _capi
+
+    lib = _capi.load()
+    header = open(os.path.join(ROOT, "include", "mdt_b200.h")).read()
+    declared = set(re.findall(r"\b(mdt_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_capi.EXPORTS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.mdt_abi_version() == _capi.MDT_ABI_VERSION
+
+
+def test_no_cpu_fallback():
+    import moleculediffusiontransformer_b200 as mdt
+    from oracle.cases import INV64
+
+    torch.manual_seed(0)
+    m = mdt.QMDiffusion(**INV64)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.sample(torch.zeros(2, 12), "cpu", cond_scale=1.0, timesteps=4)
+    with pytest.raises(RuntimeError):
+        m.unet(torch.zeros(1, 16, 64))          # parameter containers have no eager forward
+    if not torch.cuda.is_available():
+        from moleculediffusiontransformer_b200 import _capi
+        assert _capi.load().mdt_device_count() == 0
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "moleculediffusiontransformer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} references the oracle"
+
+
+def test_iter_scalars_match_reference_arithmetic():
+    """build_iter_scalars vs the oracle's restatement of ADPM2Sampler.get_sigmas / get_scale_weights."""
+    from moleculediffusiontransformer_b200 import ADPM2Sampler, KarrasSchedule, build_iter_scalars
+    from oracle import unet_oracle as orc
+
+    for n in (2, 5, 64, 100):
+        sig = KarrasSchedule(0.001, 9.0, 3.0)(n)
+        assert torch.equal(sig, orc.karras_sigmas(n))
+        tab = build_iter_scalars(sig, n, ADPM2Sampler(1.0), 0.1)
+        assert tab.shape == (n - 1, 13)
+        for i in range(n - 1):
+            s, sn = sig[i], sig[i + 1]
+            up = math.sqrt(sn ** 2 * (s ** 2 - sn ** 2) / s ** 2)
+            down = math.sqrt(sn ** 2 - up ** 2)
+            mid = ((s ** 1.0 + down ** 1.0) / 2) ** 1.0
+            assert tab[i, 0] == np.float32(s) and tab[i, 5] == np.float32(mid)
+            assert tab[i, 10] == np.float32(mid - s) and tab[i, 11] == np.float32(down - s)
+            sigmas = torch.full((1,), s)
+            assert tab[i, 2] == np.float32(torch.log(sigmas) * 0.25)
+            assert tab[i, 1] == np.float32((sigmas ** 2 + 0.1 ** 2) ** -0.5)
+
+
+def test_c_scalar_helpers_match_python():
+    from moleculediffusiontransformer_b200 import ADPM2Sampler, KarrasSchedule, _capi, build_iter_scalars
+
+    lib = _capi.load()
+    for n in (8, 64, 128):
+        sig = KarrasSchedule(0.001, 9.0, 3.0)(n)
+        c = np.zeros(n + 1, np.float32)
+        _capi.check(lib.mdt_karras_sigmas(n, 0.001, 9.0, 3.0, c.ctypes.data))
+        assert np.allclose(c[:-1], sig.numpy()[:-1], rtol=3e-7) and c[-1] == 0
+        tab = build_iter_scalars(sig, n, ADPM2Sampler(1.0), 0.1)
+        arr = (_capi.MdtIterScalars * (n - 1))()
+        s32 = sig.numpy().copy()
+        _capi.check(lib.mdt_adpm2_scalars(s32.ctypes.data, n - 1, 1.0, 0.1, arr))
+        ct = np.ctypeslib.as_array(ctypes.cast(arr, ctypes.POINTER(ctypes.c_float)), shape=(n - 1, 13))
+        assert np.allclose(ct, tab, rtol=5e-7, atol=0)
+    assert lib.mdt_karras_sigmas(1, 0.001, 9.0, 3.0, c.ctypes.data) < 0
+    assert b"num_steps" in lib.mdt_last_error()
+
+
+def test_plan_create_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import moleculediffusiontransformer_b200 as mdt
+    from moleculediffusiontransformer_b200.plan import SamplerPlan
+    from oracle.cases import INV64
+
+    torch.manual_seed(0)
+    m = mdt.QMDiffusion(**INV64)
+    with pytest.raises(RuntimeError):
+        SamplerPlan(m, "cuda:0")
+
+
+def test_shard_bounds_cover_and_balance():
+    from moleculediffusiontransformer_b200.launcher import shard_bounds
+
+    for total in (0, 1, 7, 4096, 8_000_003):
+        for ws in (1, 2, 4, 8):
+            spans = [shard_bounds(total, ws, r) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from moleculediffusiontransformer_b200.launcher import sharded_sample
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+total = 11
+seq = torch.arange(total * 3, dtype=torch.float32).reshape(total, 3)
+def run(rows, offset):  # stand-in for the CUDA plan: a pure function of (global row index, row content)
+    idx = torch.arange(offset, offset + rows.shape[0])
+    return (idx[:, None] * 7 + rows.sum(1, keepdim=True).long() + torch.arange(5)[None]).to(torch.uint8)
+full = sharded_sample(run, seq)
+if dist.get_rank() == 0:
+    want = run(seq, 0)
+    assert full is not None and torch.equal(full, want), (full, want)
+    print("OK")
+else:
+    assert full is None
+dist.destroy_process_group()
+"""
+
+
+def test_sharded_gather_world2_gloo(tmp_path):
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % {"root": ROOT, "port": port})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "OK" in outs[0][0]
