@@ -1,0 +1,229 @@
+// gemm_tma.cu -- TMA-fed tcgen05 / TMEM GEMM and implicit-GEMM Conv1d (stride 1) for sm_100a.
+//
+//   C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ res)        A, W already in the MMA operand dtype
+//
+// A is a token-major activation tensor viewed as a 3-D TMA tensor [samples][L][C]; a conv tap is a
+// shifted box in the L coordinate and TMA's out-of-bounds zero fill IS the conv's zero padding at
+// the sample boundaries.  A CTA owns a 128-row x BN tile:
+//   warp 0     one lane issues cp.async.bulk.tensor loads (A box 128 x 128 B, W box BN x 128 B) per stage
+//   warp 1     one lane issues tcgen05.mma (accumulator in TMEM), tcgen05.commit frees stages; owns TMEM
+//   warps 2-5  epilogue: tcgen05.ld -> smem staging -> coalesced bias / GELU / residual, fp32 and/or
+//              operand-dtype stores
+// 3 stages x 32 KB -> two CTAs per SM: one tile's epilogue overlaps the other's main loop.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "aload.cuh"
+#include "tc_common.cuh"
+
+namespace mdt {
+namespace tc {
+
+constexpr int T_TM = 128;
+constexpr int T_STAGES = 3;
+constexpr int T_A_BYTES = T_TM * 128;
+constexpr int T_B_BYTES = 128 * 128;
+constexpr int T_STAGE_BYTES = T_A_BYTES + T_B_BYTES;
+constexpr int T_SMEM_BYTES = T_STAGES * T_STAGE_BYTES + 1024;
+
+template <int KIND>
+__global__ void __launch_bounds__(192) gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                       const __grid_constant__ CUtensorMap tmB, const TmaGemmParams p,
+                                                       const uint32_t idesc) {
+  constexpr int KCH = (KIND == 1) ? 32 : 64;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[T_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[T_STAGES];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int BN = p.BN;
+  const int m0 = blockIdx.x * T_TM, n0 = blockIdx.y * BN;
+  const uint32_t tmem_cols = BN <= 32 ? 32u : (BN <= 64 ? 64u : 128u);
+  const int num_chunks = p.taps * p.kchunks;
+
+  if (tid == 0) {
+    for (int s = 0; s < T_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int b0, l0;
+      if (p.L >= T_TM) { const int tps = p.L / T_TM; b0 = blockIdx.x / tps; l0 = (blockIdx.x - b0 * tps) * T_TM; }
+      else { b0 = blockIdx.x * p.Sb; l0 = 0; }
+      const uint32_t tx = (uint32_t)(T_A_BYTES + BN * 128);
+      int c = 0;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        for (int kc = 0; kc < p.kchunks; ++kc, ++c) {
+          const int stage = c % T_STAGES;
+          const uint32_t phase = (uint32_t)(c / T_STAGES) & 1u;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * T_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], tx);
+          tma_load_3d(sa, &tmA, &full_bar[stage], kc * KCH, l0 + tap - p.pad, b0);
+          tma_load_2d(sa + T_A_BYTES, &tmB, &full_bar[stage], tap * p.C + kc * KCH, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    for (int c = 0; c < num_chunks; ++c) {
+      const int stage = c % T_STAGES;
+      const uint32_t phase = (uint32_t)(c / T_STAGES) & 1u;
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * T_STAGE_BYTES);
+        const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + T_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma<KIND>(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((c | k) != 0));
+        umma_commit(&empty_bar[stage]);
+        if (c == num_chunks - 1) umma_commit(&accum_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;       // tile row owned for the TMEM -> smem transfer
+    const int et = (warp - 2) * 32 + lane;
+    mbar_wait(&accum_bar, 0u);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem);
+    const int ldst = BN + 4;
+    for (int cc = 0; cc * 32 < BN; ++cc) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
+      const int ncol = min(32, BN - cc * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j * 4 < ncol)
+          *reinterpret_cast<uint4*>(stg + (size_t)r * ldst + cc * 32 + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int n4 = BN >> 2;
+    for (int idx = et; idx < T_TM * n4; idx += 128) {
+      const int rr = idx / n4, c4 = (idx - rr * n4) * 4;
+      const int mo = m0 + rr, no = n0 + c4;
+      if (mo >= p.M || no >= p.N) continue;
+      float4 o = *reinterpret_cast<const float4*>(stg + (size_t)rr * ldst + c4);
+      if (p.bias) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + no));
+        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+      }
+      if (p.act == 1) { o.x = gelu_f(o.x); o.y = gelu_f(o.y); o.z = gelu_f(o.z); o.w = gelu_f(o.w); }
+      if (p.res) {
+        const float4 rv = *reinterpret_cast<const float4*>(p.res + (size_t)mo * p.ldres + no);
+        o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+      }
+      if (p.C32) *reinterpret_cast<float4*>(p.C32 + (size_t)mo * p.ldc + no) = o;
+      if (p.Cop) {
+        if (KIND == 1) {
+          *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.Cop) + (size_t)mo * p.ldcop + no) =
+              make_uint4(to_tf32(o.x), to_tf32(o.y), to_tf32(o.z), to_tf32(o.w));
+        } else {
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.Cop) + (size_t)mo * p.ldcop + no) =
+              make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace tc
+
+int tma_pick_bn(int N) {
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  if (N % 32 == 0) return 32;
+  if (N % 16 == 0) return 16;
+  return 0;
+}
+
+bool gemm_tma_shape_ok(int kind, int C, int L, int N) {
+  const int kch = kind == 1 ? 32 : 64;
+  if (C % kch) return false;
+  if (tma_pick_bn(N) == 0) return false;
+  if (L <= 0 || (L & (L - 1))) return false;   // power of two: 128 % L == 0 or L % 128 == 0
+  return true;
+}
+
+int make_tmap_act(void* map128, const void* base, int kind, int C, int L, long long samples) {
+  tc::EncodeTiledFn fn = tc::encode_fn();
+  if (!fn) return -1;
+  const int esz = kind == 1 ? 4 : 2, kch = kind == 1 ? 32 : 64;
+  const int Lb = L >= 128 ? 128 : L, Sb = L >= 128 ? 1 : 128 / L;
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)samples};
+  cuuint64_t strides[2] = {(cuuint64_t)C * esz, (cuuint64_t)C * L * esz};
+  cuuint32_t box[3] = {(cuuint32_t)kch, (cuuint32_t)Lb, (cuuint32_t)Sb};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(map128), kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+int make_tmap_weight(void* map128, const void* base, int kind, long long K, int N, int BN) {
+  tc::EncodeTiledFn fn = tc::encode_fn();
+  if (!fn) return -1;
+  const int esz = kind == 1 ? 4 : 2, kch = kind == 1 ? 32 : 64;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)K * esz};
+  cuuint32_t box[2] = {(cuuint32_t)kch, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(map128), kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+cudaError_t init_gemm_tma() {
+  cudaError_t e = cudaFuncSetAttribute(tc::gemm_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::T_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(tc::gemm_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::T_SMEM_BYTES);
+}
+
+cudaError_t launch_gemm_tma(const void* tmA, const void* tmB, const TmaGemmParams& p, int kind, cudaStream_t s) {
+  if (p.M <= 0 || p.N <= 0) return cudaSuccess;
+  if (p.BN <= 0 || p.N % p.BN) return cudaErrorInvalidValue;
+  const uint32_t fmt = kind == 1 ? 2u : 1u;
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(tc::T_TM >> 4) << 24);
+  dim3 grid((p.M + tc::T_TM - 1) / tc::T_TM, p.N / p.BN);
+  const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(tmA);
+  const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(tmB);
+  if (kind == 1) tc::gemm_tma_kernel<1><<<grid, 192, tc::T_SMEM_BYTES, s>>>(a, b, p, idesc);
+  else tc::gemm_tma_kernel<2><<<grid, 192, tc::T_SMEM_BYTES, s>>>(a, b, p, idesc);
+  return cudaGetLastError();
+}
+
+}  // namespace mdt

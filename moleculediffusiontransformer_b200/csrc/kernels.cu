@@ -5,6 +5,7 @@
 //   * attention_kernel      per-(sample, head) softmax attention, sequence lengths <= 64
 //   * groupnorm/rownorm     two-pass statistics feeding the GEMM prologues
 //   * sampler kernels       fused ADPM2 / EDM / classifier-free-guidance update (HBM-bound)
+#include <cuda_bf16.h>
 #include <math.h>
 #include "aload.cuh"
 
@@ -182,7 +183,34 @@ cudaError_t launch_gemm_fp32(const GemmParams& p, cudaStream_t s) {
 // ================================================================================================
 // Attention core (AttentionBase.forward, modules.py:350-364): one warp per (sample, head).
 // ================================================================================================
+template <int KIND> struct AttnIO;
+template <> struct AttnIO<0> {
+  typedef float T;
+  static __device__ __forceinline__ float4 ld4(const void* p, size_t i) { return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i); }
+  static __device__ __forceinline__ void st(void* p, size_t i, float v) { reinterpret_cast<float*>(p)[i] = v; }
+};
+template <> struct AttnIO<1> {
+  typedef float T;
+  static __device__ __forceinline__ float4 ld4(const void* p, size_t i) { return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i); }
+  static __device__ __forceinline__ void st(void* p, size_t i, float v) {
+    uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    reinterpret_cast<uint32_t*>(p)[i] = r;
+  }
+};
+template <> struct AttnIO<2> {
+  typedef __nv_bfloat16 T;
+  static __device__ __forceinline__ float4 ld4(const void* p, size_t i) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + i);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  static __device__ __forceinline__ void st(void* p, size_t i, float v) { reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v); }
+};
+
+template <int KIND>
 __global__ void attention_kernel(const AttnParams p, int warps_per_cta) {
+  typedef AttnIO<KIND> IO;
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long wg = (long long)blockIdx.x * warps_per_cta + warp;
@@ -195,20 +223,19 @@ __global__ void attention_kernel(const AttnParams p, int warps_per_cta) {
   float* vs = ks + nk * dp;
   float* ss = vs + nk * d;
 
-  const float* kbase;
-  const float* vbase;
-  if (p.k_null && b >= p.n_cond) { kbase = p.k_null; vbase = p.v_null; }
-  else { kbase = p.k + (size_t)b * p.kv_sample_stride; vbase = p.v + (size_t)b * p.kv_sample_stride; }
+  const void* kbase = p.k;
+  const void* vbase = p.v;
+  size_t koff = (size_t)b * p.kv_sample_stride;
+  if (p.k_null && b >= p.n_cond) { kbase = p.k_null; vbase = p.v_null; koff = 0; }
   const int d4 = d >> 2;
   for (int idx = lane; idx < nq * d4; idx += 32) {
     const int r = idx / d4, c = (idx - r * d4) * 4;
-    *reinterpret_cast<float4*>(qs + r * dp + c) =
-        *reinterpret_cast<const float4*>(p.q + ((size_t)b * nq + r) * p.ldq + h * d + c);
+    *reinterpret_cast<float4*>(qs + r * dp + c) = IO::ld4(p.q, ((size_t)b * nq + r) * p.ldq + h * d + c);
   }
   for (int idx = lane; idx < nk * d4; idx += 32) {
     const int r = idx / d4, c = (idx - r * d4) * 4;
-    *reinterpret_cast<float4*>(ks + r * dp + c) = *reinterpret_cast<const float4*>(kbase + (size_t)r * p.ldkv + h * d + c);
-    *reinterpret_cast<float4*>(vs + r * d + c) = *reinterpret_cast<const float4*>(vbase + (size_t)r * p.ldkv + h * d + c);
+    *reinterpret_cast<float4*>(ks + r * dp + c) = IO::ld4(kbase, koff + (size_t)r * p.ldkv + h * d + c);
+    *reinterpret_cast<float4*>(vs + r * d + c) = IO::ld4(vbase, koff + (size_t)r * p.ldkv + h * d + c);
   }
   __syncwarp();
   // S = (Q K^T) * scale
@@ -241,16 +268,21 @@ __global__ void attention_kernel(const AttnParams p, int warps_per_cta) {
       const float* row = ss + i * (nk + 1);
       float acc = 0.f;
       for (int j = 0; j < nk; ++j) acc = fmaf(row[j], vs[j * d + dd], acc);
-      p.o[((size_t)b * nq + i) * p.ldo + h * d + dd] = acc;
+      IO::st(p.o, ((size_t)b * nq + i) * p.ldo + h * d + dd, acc);
     }
   }
 }
 
+cudaError_t init_prep();
 cudaError_t init_kernels() {
-  return cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = init_prep();
+  return e;
 }
 
-cudaError_t launch_attention(const AttnParams& p, cudaStream_t s) {
+cudaError_t launch_attention(const AttnParams& p, int kind, cudaStream_t s) {
   if (p.B <= 0) return cudaSuccess;
   if (p.d % 4 != 0 || p.nq > 128 || p.nk > 128) return cudaErrorInvalidValue;
   const size_t per_warp = ((((size_t)(p.nq + p.nk) * (p.d + 4) + (size_t)p.nk * p.d + (size_t)p.nq * (p.nk + 1)) + 3) & ~(size_t)3) * sizeof(float);
@@ -261,7 +293,9 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t s) {
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   const long long warps = (long long)p.B * p.heads;
   const unsigned grid = (unsigned)((warps + wpc - 1) / wpc);
-  attention_kernel<<<grid, wpc * 32, smem, s>>>(p, wpc);
+  if (kind == 0) attention_kernel<0><<<grid, wpc * 32, smem, s>>>(p, wpc);
+  else if (kind == 1) attention_kernel<1><<<grid, wpc * 32, smem, s>>>(p, wpc);
+  else attention_kernel<2><<<grid, wpc * 32, smem, s>>>(p, wpc);
   return cudaGetLastError();
 }
 

@@ -50,13 +50,14 @@ struct GemmParams {
   int ldc;
 };
 
+// Element type of q/k/v/o is selected by the launcher's `kind` (0/1: fp32, 2: bf16); strides are in ELEMENTS.
 struct AttnParams {
-  const float* q; int ldq;            // [B*nq][ldq], head h at columns h*d..
-  const float* k; const float* v;     // per-sample blocks: row (b*nk + j), leading dim ldkv
-  int ldkv; long long kv_sample_stride;  // floats between consecutive samples' K/V blocks
-  const float* k_null; const float* v_null;  // shared K/V for samples >= n_cond (classifier-free null branch)
+  const void* q; int ldq;             // [B*nq][ldq], head h at columns h*d..
+  const void* k; const void* v;       // per-sample blocks: row (b*nk + j), leading dim ldkv
+  int ldkv; long long kv_sample_stride;  // elements between consecutive samples' K/V blocks
+  const void* k_null; const void* v_null;  // shared K/V for samples >= n_cond (classifier-free null branch)
   int n_cond;
-  float* o; int ldo;
+  void* o; int ldo;
   int B, nq, nk, heads, d;
   float scale;
 };
@@ -102,7 +103,8 @@ struct StepParams {
 cudaError_t init_kernels();
 cudaError_t init_gemm_tc();
 cudaError_t launch_gemm_fp32(const GemmParams& p, cudaStream_t s);
-cudaError_t launch_attention(const AttnParams& p, cudaStream_t s);
+// kind: 0 fp32 in/out, 1 fp32 in / tf32-rounded fp32 out, 2 bf16 in/out
+cudaError_t launch_attention(const AttnParams& p, int kind, cudaStream_t s);
 cudaError_t launch_groupnorm_stats(const NormStatsParams& p, cudaStream_t s);
 cudaError_t launch_rownorm_stats(const NormStatsParams& p, cudaStream_t s);
 // out[b, o, co] = bias[co] + sum_j Y[b, i_j, k_j * Cout + co] (+ add[b, o, co]);  ConvTranspose1d(k=2f, s=f, p=f/2)
@@ -132,6 +134,40 @@ cudaError_t launch_to_token_major(const float* in, float* out, int B, int P, int
                                   cudaStream_t s);
 cudaError_t launch_cfg_mix_to_bpl(const float* net, float* out, int B, int P, int L, float cond_scale, int cfg,
                                   cudaStream_t s);
+
+// ---- operand preparation (prep.cu): normalise + activate once, write the MMA operand dtype -----------
+// kind: 1 = tf32 (fp32 storage, round-to-nearest tf32), 2 = bf16
+struct GnApplyParams {
+  const float* src0; const float* src1; int c0, c1; float scale1;   // concat of two fp32 token-major sources
+  int L, groups; float eps;
+  const float* aff; int aff_call_stride; const int* call_idx;       // per-channel (A, B) table or null
+  int silu;
+  void* out;   // normalised operand [B*L][C]
+  void* raw;   // optional un-normalised operand copy (1x1 skip projection input) or null
+  int B;
+};
+cudaError_t launch_gn_apply(const GnApplyParams& p, int kind, cudaStream_t s);
+bool gn_apply_supported(int L, int C, int groups);
+struct LnApplyParams { const float* src; int C; float eps; void* out; long long rows; };
+cudaError_t launch_ln_apply(const LnApplyParams& p, int kind, cudaStream_t s);
+
+// ---- TMA-fed tcgen05 GEMM (gemm_tma.cu): both operands arrive by cp.async.bulk.tensor ------------------
+struct TmaGemmParams {
+  int M, N, BN;
+  int taps, pad, kchunks, C;  // K loop = taps x kchunks chunks of 128 bytes; weight column = tap * C + kc * KCH
+  int L, Lb, Sb;              // positions per sample; TMA box = (KCH, Lb, Sb), Lb * Sb == 128 rows
+  const float* bias; int act;
+  const float* res; int ldres;
+  float* C32; int ldc;        // fp32 output (residual stream) or null
+  void* Cop; int ldcop;       // operand-dtype copy of the same values (next GEMM / attention input) or null
+};
+// 128-byte CUtensorMap blobs (64-byte aligned) built on the host
+int make_tmap_act(void* map128, const void* base, int kind, int C, int L, long long samples);
+int make_tmap_weight(void* map128, const void* base, int kind, long long K, int N, int BN);
+int tma_pick_bn(int N);
+bool gemm_tma_shape_ok(int kind, int C, int L, int N);
+cudaError_t init_gemm_tma();
+cudaError_t launch_gemm_tma(const void* tmA, const void* tmB, const TmaGemmParams& p, int kind, cudaStream_t s);
 
 // ---- tensor-core GEMM (gemm_tc.cu) --------------------------------------------------------------
 // kind: 1 = tf32, 2 = bf16.  Wtc must hold the weights pre-converted by convert_weights_tc().

@@ -55,7 +55,7 @@ struct MdtError {
 // ------------------------------------------------------------------------------------------------
 // program representation
 // ------------------------------------------------------------------------------------------------
-enum OpType { OP_GEMM, OP_GN_STATS, OP_ROW_STATS, OP_ATTN, OP_UPGATHER, OP_PERMUTE };
+enum OpType { OP_GEMM, OP_GN_STATS, OP_ROW_STATS, OP_ATTN, OP_UPGATHER, OP_PERMUTE, OP_GN_APPLY, OP_LN_APPLY, OP_GEMM_TMA };
 
 struct Op {
   OpType type = OP_GEMM;
@@ -63,6 +63,12 @@ struct Op {
   GemmParams g{};
   NormStatsParams ns{};
   AttnParams at{};
+  int attn_kind = 0;   // storage type of q/k/v/o (0 fp32, 1 tf32-rounded fp32, 2 bf16)
+  GnApplyParams ga{};
+  LnApplyParams la{};
+  TmaGemmParams tg{};
+  alignas(64) unsigned char tmA[128];
+  alignas(64) unsigned char tmB[128];
   bool cross = false;  // attention reads the precomputed conditioning K/V
   int cross_layer = -1;
   // upsample gather / permute
@@ -87,6 +93,8 @@ struct CrossLayer {
   const float* wkv; const float* bkv;  // folded norm_context -> to_kv  [2*Hd][F], [2*Hd]
   float* kv_cond;                      // [max_batch * n_ctx_max][2*Hd]
   float* kv_null;                      // [n_ctx_max][2*Hd]
+  void* kv_cond_op = nullptr;          // operand-dtype copies read by the attention kernel in the tensor-core modes
+  void* kv_null_op = nullptr;
 };
 
 struct mdt_plan {
@@ -257,8 +265,43 @@ struct Builder {
     Op& op = prog.back(); op.tap = name; op.tap_ptr = ptr; op.tap_rps = rps; op.tap_c = c;
   }
 
+  // ---- TMA path helpers (tensor-core precisions only)
+  bool tma() const { return pl.prec != MDT_PREC_FP32; }
+  int esz() const { return pl.prec == MDT_PREC_BF16 ? 2 : 4; }
+  void* op_off(void* base, size_t elems) const { return reinterpret_cast<char*>(base) + elems * (size_t)esz(); }
+  bool tma_ok(int C, int L, int N) const { return tma() && gemm_tma_shape_ok(pl.prec, C, L, N); }
+
+  void emit_gn_apply(std::vector<Op>& prog, const Src& in, int L, int groups, float eps, const float* aff, int aff_stride,
+                     const int* call_idx, int silu, void* out, void* raw) {
+    Op op; op.type = OP_GN_APPLY;
+    op.ga.src0 = in.p0; op.ga.src1 = in.p1; op.ga.c0 = in.c0; op.ga.c1 = in.c1; op.ga.scale1 = in.scale1;
+    op.ga.L = L; op.ga.groups = groups; op.ga.eps = eps; op.ga.aff = aff; op.ga.aff_call_stride = aff_stride;
+    op.ga.call_idx = call_idx; op.ga.silu = silu; op.ga.out = out; op.ga.raw = raw; op.ga.B = 0;
+    emit(prog, op);
+  }
+  void emit_ln_apply(std::vector<Op>& prog, const float* src, int C, int L, void* out) {
+    Op op; op.type = OP_LN_APPLY; op.rps = L;
+    op.la.src = src; op.la.C = C; op.la.eps = 1e-5f; op.la.out = out; op.la.rows = 0;
+    emit(prog, op);
+  }
+  // A: operand-dtype activation [Beff_max * L][C]; dW32: packed fp32 weights [N][taps * C] already on the device
+  void emit_gemm_tma(std::vector<Op>& prog, const void* A, int C, int L, int taps, const float* dW32, const float* bias, int N,
+                     int act, const float* res, float* C32, void* Cop, int ldcop = 0) {
+    Op op; op.type = OP_GEMM_TMA; op.rps = L;
+    const int kch = pl.prec == MDT_PREC_TF32 ? 32 : 64;
+    TmaGemmParams& g = op.tg;
+    g.M = 0; g.N = N; g.BN = tma_pick_bn(N); g.taps = taps; g.pad = taps / 2; g.kchunks = C / kch; g.C = C;
+    g.L = L; g.Lb = L >= 128 ? 128 : L; g.Sb = L >= 128 ? 1 : 128 / L;
+    g.bias = bias; g.act = act; g.res = res; g.ldres = N; g.C32 = C32; g.ldc = N; g.Cop = Cop; g.ldcop = ldcop ? ldcop : N;
+    const void* wop = tc_copy(dW32, (size_t)N * taps * C);
+    if (make_tmap_act(op.tmA, A, pl.prec, C, L, (long long)pl.Beff_max) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(activation C=%d L=%d) failed", C, L);
+    if (make_tmap_weight(op.tmB, wop, pl.prec, (long long)taps * C, N, g.BN) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(weight K=%d N=%d) failed", taps * C, N);
+    emit(prog, op);
+  }
+
   // ResnetBlock1d (modules.py:145-205).  Returns the output buffer (acquired from the pool).
-  float* resnet(std::vector<Op>& prog, const std::string& pre, const Src& in, int L, int Cout, int groups) {
+  float* resnet(std::vector<Op>& prog, const std::string& pre, const Src& in, int L, int Cout, int groups,
+                float* forced_out = nullptr) {
     const int Cin = in.C();
     const int M = pl.cfg.mapping_features;
     // block1: GN(groups) -> SiLU -> conv3
@@ -269,9 +312,18 @@ struct Builder {
     auto w1 = pack_conv(T(pre + "block1.project.weight", (int64_t)Cout * Cin * 3), Cout, Cin, 3);
     const float* d_w1 = upload(w1);
     const float* d_b1 = upload(T(pre + "block1.project.bias", Cout), Cout);
-    gn_stats(prog, in, L, groups, 1e-5f);
+    const bool ok1 = tma_ok(Cin, L, Cout) && gn_apply_supported(L, Cin, groups);
+    const bool ok2 = tma_ok(Cout, L, Cout) && gn_apply_supported(L, Cout, groups);
+    const bool proj = has(pre + "to_out.weight");
     float* h1 = acquire();
-    {
+    float* a1 = nullptr; float* raw = nullptr;
+    if (ok1) {
+      a1 = acquire();
+      if (proj) raw = acquire();
+      emit_gn_apply(prog, in, L, groups, 1e-5f, d_aff1, 0, nullptr, 1, a1, raw);
+      emit_gemm_tma(prog, a1, Cin, L, 3, d_w1, d_b1, Cout, 0, nullptr, h1, nullptr);
+    } else {
+      gn_stats(prog, in, L, groups, 1e-5f);
       ALoad a = make_aload(in, L, L, 3, 1, 1);
       a.stats = pl.gn_stats; a.stats_mode = 2; a.groups = groups; a.cpg = Cin / groups; a.aff = d_aff1; a.silu = 1;
       emit(prog, gemm_op(a, d_w1, tc_copy(d_w1, w1.size()), d_b1, Cout, 0, nullptr, h1, L));
@@ -287,13 +339,17 @@ struct Builder {
     f.aff = dalloc((size_t)pl.max_calls * 2 * Cout);
     pl.films.push_back(f);
     // residual path
-    float* out = acquire();
+    float* out = forced_out ? forced_out : acquire();
     const float* res;
-    if (has(pre + "to_out.weight")) {
+    if (proj) {
       const float* d_wo = upload(T(pre + "to_out.weight", (int64_t)Cout * Cin), (size_t)Cout * Cin);
       const float* d_bo = upload(T(pre + "to_out.bias", Cout), Cout);
-      ALoad a = make_aload(in, L, L, 1, 1, 0);
-      emit(prog, gemm_op(a, d_wo, tc_copy(d_wo, (size_t)Cout * Cin), d_bo, Cout, 0, nullptr, out, L));
+      if (ok1) {
+        emit_gemm_tma(prog, raw, Cin, L, 1, d_wo, d_bo, Cout, 0, nullptr, out, nullptr);
+      } else {
+        ALoad a = make_aload(in, L, L, 1, 1, 0);
+        emit(prog, gemm_op(a, d_wo, tc_copy(d_wo, (size_t)Cout * Cin), d_bo, Cout, 0, nullptr, out, L));
+      }
       res = out;
     } else {
       if (in.c1 != 0 || Cin != Cout) raise(MDT_ERR_INVALID, "resnet '%s': identity skip needs Cin == Cout", pre.c_str());
@@ -301,71 +357,103 @@ struct Builder {
     }
     // block2: GN -> FiLM -> SiLU -> conv3, + residual
     Src hs{h1, Cout, nullptr, 0, 1.f};
-    gn_stats(prog, hs, L, groups, 1e-5f);
     auto w2 = pack_conv(T(pre + "block2.project.weight", (int64_t)Cout * Cout * 3), Cout, Cout, 3);
     const float* d_w2 = upload(w2);
     const float* d_b2 = upload(T(pre + "block2.project.bias", Cout), Cout);
-    {
+    if (ok2) {
+      float* a2 = a1 ? a1 : acquire();   // a1 is dead once conv1 has run
+      emit_gn_apply(prog, hs, L, groups, 1e-5f, f.aff, 2 * Cout, pl.d_call, 1, a2, nullptr);
+      emit_gemm_tma(prog, a2, Cout, L, 3, d_w2, d_b2, Cout, 0, res, out, nullptr);
+      if (!a1) release(a2);
+    } else {
+      gn_stats(prog, hs, L, groups, 1e-5f);
       ALoad a = make_aload(hs, L, L, 3, 1, 1);
       a.stats = pl.gn_stats; a.stats_mode = 2; a.groups = groups; a.cpg = Cout / groups;
       a.aff = f.aff; a.aff_call_stride = 2 * Cout; a.call_idx = pl.d_call; a.silu = 1;
       emit(prog, gemm_op(a, d_w2, tc_copy(d_w2, w2.size()), d_b2, Cout, 0, res, out, L));
     }
+    if (a1) release(a1);
+    if (raw) release(raw);
     release(h1);
     return out;
   }
 
-  // Transformer1d (modules.py:469-524).  ctx_features == 0 -> self-attention only.
-  float* transformer(std::vector<Op>& prog, const std::string& pre, const float* x, int L, int C, bool with_ctx) {
+  // Transformer1d (modules.py:469-524).  with_ctx == false -> self-attention only.
+  // out_op (optional): receives an operand-dtype copy of the output when the tensor-core path is taken.
+  float* transformer(std::vector<Op>& prog, const std::string& pre, const float* x, int L, int C, bool with_ctx,
+                     void** out_op = nullptr) {
     const int Hd = pl.Hd, heads = pl.cfg.heads, d = pl.cfg.head_features, F = pl.F;
+    const int mid = C * pl.cfg.ff_multiplier;
+    if (out_op) *out_op = nullptr;
+    const bool fast = tma_ok(C, L, C) && gn_apply_supported(L, C, 32) && tma_ok(C, L, 3 * Hd) && tma_ok(C, L, Hd) &&
+                      tma_ok(Hd, L, C) && tma_ok(C, L, mid) && tma_ok(mid, L, C) && C <= 1024;
+    const int akind = fast ? pl.prec : 0;
     // to_in: GroupNorm(32, eps 1e-6) folded into the 1x1 conv
     std::vector<float> wi(T(pre + "to_in.1.weight", (int64_t)C * C), T(pre + "to_in.1.weight", (int64_t)C * C) + (size_t)C * C);
     std::vector<float> bi(T(pre + "to_in.1.bias", C), T(pre + "to_in.1.bias", C) + C);
     fold_affine(wi, bi, C, C, T(pre + "to_in.0.weight", C), T(pre + "to_in.0.bias", C));
     const float* d_wi = upload(wi); const float* d_bi = upload(bi);
     Src xs{x, C, nullptr, 0, 1.f};
-    gn_stats(prog, xs, L, 32, 1e-6f);
     float* t = acquire();
-    {
+    float* tn = fast ? acquire() : nullptr;   // normalised / raw operand copies of the token stream
+    if (fast) {
+      emit_gn_apply(prog, xs, L, 32, 1e-6f, nullptr, 0, nullptr, 0, tn, nullptr);
+      emit_gemm_tma(prog, tn, C, L, 1, d_wi, d_bi, C, 0, nullptr, t, nullptr);
+    } else {
+      gn_stats(prog, xs, L, 32, 1e-6f);
       ALoad a = make_aload(xs, L, L, 1, 1, 0);
       a.stats = pl.gn_stats; a.stats_mode = 2; a.groups = 32; a.cpg = C / 32;
       emit(prog, gemm_op(a, d_wi, tc_copy(d_wi, wi.size()), d_bi, C, 0, nullptr, t, L));
     }
     Src ts{t, C, nullptr, 0, 1.f};
-    for (int i = 0; has(pre + "blocks." + std::to_string(i) + ".attention.to_q.weight"); ++i) {
+    int nblocks = 0;
+    while (has(pre + "blocks." + std::to_string(nblocks) + ".attention.to_q.weight")) ++nblocks;
+    for (int i = 0; i < nblocks; ++i) {
       const std::string bp = pre + "blocks." + std::to_string(i) + ".";
+      const bool has_cross = has(bp + "cross_attention.to_q.weight");
       // ---- self attention: fused QKV projection on LN statistics shared by norm / norm_context
       {
         const std::string ap = bp + "attention.";
         std::vector<float> w((size_t)3 * Hd * C), b((size_t)3 * Hd, 0.f);
-        memcpy(w.data(), T(ap + "to_q.weight", (int64_t)Hd * C), (size_t)Hd * C * sizeof(float));
-        memcpy(w.data() + (size_t)Hd * C, T(ap + "to_kv.weight", (int64_t)2 * Hd * C), (size_t)2 * Hd * C * sizeof(float));
         {
-          std::vector<float> wq(w.begin(), w.begin() + (size_t)Hd * C), bq(Hd, 0.f);
+          std::vector<float> wq(T(ap + "to_q.weight", (int64_t)Hd * C), T(ap + "to_q.weight", (int64_t)Hd * C) + (size_t)Hd * C), bq(Hd, 0.f);
           fold_affine(wq, bq, Hd, C, T(ap + "norm.weight", C), T(ap + "norm.bias", C));
-          std::vector<float> wkv(w.begin() + (size_t)Hd * C, w.end()), bkv(2 * Hd, 0.f);
+          std::vector<float> wkv(T(ap + "to_kv.weight", (int64_t)2 * Hd * C), T(ap + "to_kv.weight", (int64_t)2 * Hd * C) + (size_t)2 * Hd * C), bkv(2 * Hd, 0.f);
           fold_affine(wkv, bkv, 2 * Hd, C, T(ap + "norm_context.weight", C), T(ap + "norm_context.bias", C));
           std::copy(wq.begin(), wq.end(), w.begin()); std::copy(wkv.begin(), wkv.end(), w.begin() + (size_t)Hd * C);
           std::copy(bq.begin(), bq.end(), b.begin()); std::copy(bkv.begin(), bkv.end(), b.begin() + Hd);
         }
         const float* d_w = upload(w); const float* d_b = upload(b);
-        row_stats(prog, t, C, L, pl.row_stats);
-        ALoad a = make_aload(ts, L, L, 1, 1, 0);
-        a.stats = pl.row_stats; a.stats_mode = 1;
-        emit(prog, gemm_op(a, d_w, tc_copy(d_w, w.size()), d_b, 3 * Hd, 0, nullptr, pl.qkv, L));
-        Op at; at.type = OP_ATTN;
-        at.at.q = pl.qkv; at.at.ldq = 3 * Hd; at.at.k = pl.qkv + Hd; at.at.v = pl.qkv + 2 * Hd; at.at.ldkv = 3 * Hd;
+        if (fast) {
+          emit_ln_apply(prog, t, C, L, tn);
+          emit_gemm_tma(prog, tn, C, L, 1, d_w, d_b, 3 * Hd, 0, nullptr, nullptr, pl.qkv);
+        } else {
+          row_stats(prog, t, C, L, pl.row_stats);
+          ALoad a = make_aload(ts, L, L, 1, 1, 0);
+          a.stats = pl.row_stats; a.stats_mode = 1;
+          emit(prog, gemm_op(a, d_w, tc_copy(d_w, w.size()), d_b, 3 * Hd, 0, nullptr, pl.qkv, L));
+        }
+        Op at; at.type = OP_ATTN; at.attn_kind = akind;
+        at.at.q = pl.qkv; at.at.ldq = 3 * Hd;
+        at.at.k = fast ? op_off(pl.qkv, Hd) : (void*)(pl.qkv + Hd);
+        at.at.v = fast ? op_off(pl.qkv, 2 * Hd) : (void*)(pl.qkv + 2 * Hd);
+        at.at.ldkv = 3 * Hd;
         at.at.kv_sample_stride = (long long)L * 3 * Hd; at.at.k_null = nullptr; at.at.v_null = nullptr; at.at.n_cond = 0;
         at.at.o = pl.att; at.at.ldo = Hd; at.at.nq = L; at.at.nk = L; at.at.heads = heads; at.at.d = d;
         at.at.scale = 1.0f / sqrtf((float)d);
         emit(prog, at);
         const float* d_wo = upload(T(ap + "attention.to_out.weight", (int64_t)C * Hd), (size_t)C * Hd);
         const float* d_bo = upload(T(ap + "attention.to_out.bias", C), C);
-        Src as{pl.att, Hd, nullptr, 0, 1.f};
-        emit(prog, gemm_op(make_aload(as, L, L, 1, 1, 0), d_wo, tc_copy(d_wo, (size_t)C * Hd), d_bo, C, 0, t, t, L));
+        if (fast) {
+          // without a cross-attention stage the raw operand copy of the new token stream feeds FF1 directly
+          emit_gemm_tma(prog, pl.att, Hd, L, 1, d_wo, d_bo, C, 0, t, t, has_cross ? nullptr : (void*)tn);
+        } else {
+          Src as{pl.att, Hd, nullptr, 0, 1.f};
+          emit(prog, gemm_op(make_aload(as, L, L, 1, 1, 0), d_wo, tc_copy(d_wo, (size_t)C * Hd), d_bo, C, 0, t, t, L));
+        }
       }
       // ---- cross attention onto the conditioning embedding (K/V are loop invariant: precomputed per sample)
-      if (has(bp + "cross_attention.to_q.weight")) {
+      if (has_cross) {
         if (!with_ctx) raise(MDT_ERR_INVALID, "unexpected cross_attention under '%s'", bp.c_str());
         const std::string ap = bp + "cross_attention.";
         std::vector<float> wq(T(ap + "to_q.weight", (int64_t)Hd * C), T(ap + "to_q.weight", (int64_t)Hd * C) + (size_t)Hd * C), bq(Hd, 0.f);
@@ -377,40 +465,70 @@ struct Builder {
         cl.wkv = upload(wkv); cl.bkv = upload(bkv);
         cl.kv_cond = dalloc((size_t)pl.Bmax * pl.cfg.ctx_max_length * 2 * Hd);
         cl.kv_null = dalloc((size_t)pl.cfg.ctx_max_length * 2 * Hd);
+        if (fast) {
+          cl.kv_cond_op = dalloc((size_t)pl.Bmax * pl.cfg.ctx_max_length * 2 * Hd);   // sized in floats; bf16 uses half
+          cl.kv_null_op = dalloc((size_t)pl.cfg.ctx_max_length * 2 * Hd);
+        }
         const int layer = (int)pl.cross.size();
         pl.cross.push_back(cl);
-        row_stats(prog, t, C, L, pl.row_stats);
-        ALoad a = make_aload(ts, L, L, 1, 1, 0);
-        a.stats = pl.row_stats; a.stats_mode = 1;
-        emit(prog, gemm_op(a, d_wq, tc_copy(d_wq, wq.size()), d_bq, Hd, 0, nullptr, pl.qc, L));
-        Op at; at.type = OP_ATTN; at.cross = true; at.cross_layer = layer;
-        at.at.q = pl.qc; at.at.ldq = Hd; at.at.k = cl.kv_cond; at.at.v = cl.kv_cond + Hd; at.at.ldkv = 2 * Hd;
-        at.at.k_null = cl.kv_null; at.at.v_null = cl.kv_null + Hd;
+        if (fast) {
+          emit_ln_apply(prog, t, C, L, tn);
+          emit_gemm_tma(prog, tn, C, L, 1, d_wq, d_bq, Hd, 0, nullptr, nullptr, pl.qc);
+        } else {
+          row_stats(prog, t, C, L, pl.row_stats);
+          ALoad a = make_aload(ts, L, L, 1, 1, 0);
+          a.stats = pl.row_stats; a.stats_mode = 1;
+          emit(prog, gemm_op(a, d_wq, tc_copy(d_wq, wq.size()), d_bq, Hd, 0, nullptr, pl.qc, L));
+        }
+        Op at; at.type = OP_ATTN; at.cross = true; at.cross_layer = layer; at.attn_kind = akind;
+        at.at.q = pl.qc; at.at.ldq = Hd; at.at.ldkv = 2 * Hd;
+        if (fast) {
+          at.at.k = cl.kv_cond_op; at.at.v = op_off(cl.kv_cond_op, Hd);
+          at.at.k_null = cl.kv_null_op; at.at.v_null = op_off(cl.kv_null_op, Hd);
+        } else {
+          at.at.k = cl.kv_cond; at.at.v = cl.kv_cond + Hd; at.at.k_null = cl.kv_null; at.at.v_null = cl.kv_null + Hd;
+        }
         at.at.o = pl.att; at.at.ldo = Hd; at.at.nq = L; at.at.heads = heads; at.at.d = d;
         at.at.scale = 1.0f / sqrtf((float)d);
         emit(prog, at);
         const float* d_wo = upload(T(ap + "attention.to_out.weight", (int64_t)C * Hd), (size_t)C * Hd);
         const float* d_bo = upload(T(ap + "attention.to_out.bias", C), C);
-        Src as{pl.att, Hd, nullptr, 0, 1.f};
-        emit(prog, gemm_op(make_aload(as, L, L, 1, 1, 0), d_wo, tc_copy(d_wo, (size_t)C * Hd), d_bo, C, 0, t, t, L));
+        if (fast) {
+          emit_gemm_tma(prog, pl.att, Hd, L, 1, d_wo, d_bo, C, 0, t, t, tn);
+        } else {
+          Src as{pl.att, Hd, nullptr, 0, 1.f};
+          emit(prog, gemm_op(make_aload(as, L, L, 1, 1, 0), d_wo, tc_copy(d_wo, (size_t)C * Hd), d_bo, C, 0, t, t, L));
+        }
       }
       // ---- feed forward (no norm): Linear -> GELU -> Linear, + residual
       {
-        const int mid = C * pl.cfg.ff_multiplier;
         const float* d_w0 = upload(T(bp + "feed_forward.0.weight", (int64_t)mid * C), (size_t)mid * C);
         const float* d_b0 = upload(T(bp + "feed_forward.0.bias", mid), mid);
         const float* d_w2 = upload(T(bp + "feed_forward.2.weight", (int64_t)C * mid), (size_t)C * mid);
         const float* d_b2 = upload(T(bp + "feed_forward.2.bias", C), C);
-        emit(prog, gemm_op(make_aload(ts, L, L, 1, 1, 0), d_w0, tc_copy(d_w0, (size_t)mid * C), d_b0, mid, 1, nullptr, pl.ff, L));
-        Src fs{pl.ff, mid, nullptr, 0, 1.f};
-        emit(prog, gemm_op(make_aload(fs, L, L, 1, 1, 0), d_w2, tc_copy(d_w2, (size_t)C * mid), d_b2, C, 0, t, t, L));
+        if (fast) {
+          emit_gemm_tma(prog, tn, C, L, 1, d_w0, d_b0, mid, 1, nullptr, nullptr, pl.ff);
+          // the last block's output is consumed by to_out as a raw operand: write the copy here
+          emit_gemm_tma(prog, pl.ff, mid, L, 1, d_w2, d_b2, C, 0, t, t, (i == nblocks - 1) ? (void*)tn : nullptr);
+        } else {
+          emit(prog, gemm_op(make_aload(ts, L, L, 1, 1, 0), d_w0, tc_copy(d_w0, (size_t)mid * C), d_b0, mid, 1, nullptr, pl.ff, L));
+          Src fs{pl.ff, mid, nullptr, 0, 1.f};
+          emit(prog, gemm_op(make_aload(fs, L, L, 1, 1, 0), d_w2, tc_copy(d_w2, (size_t)C * mid), d_b2, C, 0, t, t, L));
+        }
       }
     }
     const float* d_wo = upload(T(pre + "to_out.1.weight", (int64_t)C * C), (size_t)C * C);
     const float* d_bo = upload(T(pre + "to_out.1.bias", C), C);
     float* out = acquire();
-    emit(prog, gemm_op(make_aload(ts, L, L, 1, 1, 0), d_wo, tc_copy(d_wo, (size_t)C * C), d_bo, C, 0, nullptr, out, L));
+    if (fast && nblocks > 0) {
+      void* oc = nullptr;
+      if (out_op) { oc = acquire(); *out_op = oc; }
+      emit_gemm_tma(prog, tn, C, L, 1, d_wo, d_bo, C, 0, nullptr, out, oc);
+    } else {
+      emit(prog, gemm_op(make_aload(ts, L, L, 1, 1, 0), d_wo, tc_copy(d_wo, (size_t)C * C), d_bo, C, 0, nullptr, out, L));
+    }
     release(t);
+    if (tn) release(tn);
     return out;
   }
 
@@ -432,7 +550,7 @@ struct Builder {
     size_t S = (size_t)c.length * std::max(Cin0, std::max(c.in_channels, c.out_channels));
     size_t Sqkv = 4, Satt = 4, Sff = 4, Sup = 4; int Lmax = c.length;
     for (int i = 0; i <= nlev; ++i) {
-      S = std::max(S, (size_t)Ll[i] * Cl[i] * (i > 0 ? 1 : 1));
+      S = std::max(S, (size_t)Ll[i] * Cl[i] * (i > 0 ? 2 : 1));   // up-block resnets see cat(x, skip): 2 * C channels
       if (i > 0) {
         Sqkv = std::max(Sqkv, (size_t)Ll[i] * 3 * pl.Hd);
         Satt = std::max(Satt, (size_t)Ll[i] * pl.Hd);
@@ -573,8 +691,9 @@ struct Builder {
         set_tap(prog, "up" + std::to_string(u) + ".pre", t, Li, Ci);
         release(xcur); xcur = t;
       }
+      void* xop = nullptr;
       if (c.attentions[i] > 0) {
-        float* t = transformer(prog, up + "transformer.", xcur, Li, Ci, true);
+        float* t = transformer(prog, up + "transformer.", xcur, Li, Ci, true, &xop);
         set_tap(prog, "up" + std::to_string(u) + ".tr", t, Li, Ci);
         release(xcur); xcur = t;
       }
@@ -587,8 +706,13 @@ struct Builder {
           for (int kk = 0; kk < K2; ++kk) wp[((size_t)kk * Co + co) * Ci + ci] = wt[((size_t)ci * Co + co) * K2 + kk];
       const float* d_wp = upload(wp);
       const float* d_bu = upload(T(up + "upsample.bias", Co), Co);
-      Src s{xcur, Ci, nullptr, 0, 1.f};
-      emit(prog, gemm_op(make_aload(s, Li, Li, 1, 1, 0), d_wp, tc_copy(d_wp, wp.size()), nullptr, K2 * Co, 0, nullptr, pl.upy, Li));
+      if (xop && tma_ok(Ci, Li, K2 * Co)) {
+        emit_gemm_tma(prog, xop, Ci, Li, 1, d_wp, nullptr, K2 * Co, 0, nullptr, pl.upy, nullptr);
+      } else {
+        Src s{xcur, Ci, nullptr, 0, 1.f};
+        emit(prog, gemm_op(make_aload(s, Li, Li, 1, 1, 0), d_wp, tc_copy(d_wp, wp.size()), nullptr, K2 * Co, 0, nullptr, pl.upy, Li));
+      }
+      if (xop) release(reinterpret_cast<float*>(xop));
       float* y = acquire();
       Op op; op.type = OP_UPGATHER; op.in0 = pl.upy; op.in1 = d_bu; op.in2 = (i == 0) ? skip0 : nullptr; op.out = y;
       op.i0 = Li; op.i1 = Co; op.i2 = f;
@@ -605,15 +729,9 @@ struct Builder {
     }
     {
       Src s{xcur, Cin0, nullptr, 0, 1.f};
-      float* r = resnet(prog, U + "to_out.block.", s, c.length, c.out_channels, 1);
-      // the program must end in pl.net_out: retarget the last GEMM(s) of the block
-      for (auto it = prog.rbegin(); it != prog.rend(); ++it) {
-        if (it->type == OP_GEMM && it->g.C == r) { it->g.C = pl.net_out; if (it->g.res == r) it->g.res = pl.net_out; }
-        else if (it->type == OP_GEMM) break;
-        else if (it->type != OP_GN_STATS) break;
-      }
+      resnet(prog, U + "to_out.block.", s, c.length, c.out_channels, 1, pl.net_out);   // the program ends in pl.net_out
       set_tap(prog, "to_out", pl.net_out, c.length, c.out_channels);
-      release(xcur); release(r);
+      release(xcur);
     }
     CK(cudaDeviceSynchronize());
   }
@@ -638,8 +756,11 @@ static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_con
       case OP_ATTN: {
         AttnParams a = op.at; a.B = Beff;
         if (op.cross) { a.nk = n_ctx; a.kv_sample_stride = (long long)n_ctx * a.ldkv; a.n_cond = n_cond; }
-        CK(launch_attention(a, s)); pl.launches++; break;
+        CK(launch_attention(a, op.attn_kind, s)); pl.launches++; break;
       }
+      case OP_GN_APPLY: { GnApplyParams g = op.ga; g.B = Beff; CK(launch_gn_apply(g, pl.prec, s)); pl.launches++; break; }
+      case OP_LN_APPLY: { LnApplyParams l = op.la; l.rows = (long long)Beff * op.rps; CK(launch_ln_apply(l, pl.prec, s)); pl.launches++; break; }
+      case OP_GEMM_TMA: { TmaGemmParams g = op.tg; g.M = Beff * op.rps; CK(launch_gemm_tma(op.tmA, op.tmB, g, pl.prec, s)); pl.launches++; break; }
       case OP_UPGATHER: CK(launch_upsample_gather(op.in0, op.in1, op.in2, op.out, Beff, op.i0, op.i1, op.i2, s)); pl.launches++; break;
       case OP_PERMUTE: CK(launch_patch_permute(op.in0, op.out, Beff, op.i0, op.i1, op.i2, op.i3, s)); pl.launches++; break;
     }
@@ -695,10 +816,12 @@ static void run_context(mdt_plan& pl, const float* cond_dev, int Bc, int n_ctx, 
     GemmParams g = dense(pl.emb, F, cl.wkv, cl.bkv, 2 * Hd, Bc * n_ctx, 0, cl.kv_cond, false);
     g.a.stats = pl.emb_stats; g.a.stats_mode = 1;
     CK(launch_gemm_fp32(g, s)); pl.launches++;
+    if (cl.kv_cond_op) { CK(convert_weights_tc(cl.kv_cond, cl.kv_cond_op, (long long)Bc * n_ctx * 2 * Hd, pl.prec, s)); pl.launches++; }
     if (cfg) {
       GemmParams gn = dense(pl.w_null_emb, F, cl.wkv, cl.bkv, 2 * Hd, n_ctx, 0, cl.kv_null, false);
       gn.a.stats = pl.emb_null_stats; gn.a.stats_mode = 1;
       CK(launch_gemm_fp32(gn, s)); pl.launches++;
+      if (cl.kv_null_op) { CK(convert_weights_tc(cl.kv_null, cl.kv_null_op, (long long)n_ctx * 2 * Hd, pl.prec, s)); pl.launches++; }
     }
   }
 }
@@ -786,6 +909,7 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
     CK(cudaSetDevice(device));
     CK(init_kernels());
     CK(init_gemm_tc());
+    CK(init_gemm_tma());
     pl->cfg = *cfg; pl->device = device; pl->prec = cfg->precision;
     pl->P = cfg->in_channels; pl->L0 = cfg->length; pl->Hd = cfg->heads * cfg->head_features; pl->F = cfg->ctx_features;
     pl->Bmax = cfg->max_batch; pl->Beff_max = 2 * cfg->max_batch;

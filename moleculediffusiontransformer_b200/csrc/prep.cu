@@ -1,0 +1,162 @@
+// prep.cu -- operand preparation kernels for the TMA-fed GEMMs (HBM-bound, one pass):
+//   gn_apply : GroupNorm statistics + normalise + per-channel affine (gamma/beta with FiLM folded) + SiLU over a
+//              (possibly concatenated) fp32 token-major tensor, written once in the MMA operand dtype.
+//              One CTA owns whole samples, so statistics never leave shared memory.
+//   ln_apply : LayerNorm (no affine: gamma/beta are folded into the following projection) per row.
+#include <cuda_bf16.h>
+#include "aload.cuh"
+#include "tc_common.cuh"
+
+namespace mdt {
+
+template <int KIND>
+__device__ __forceinline__ void store_op4(void* base, size_t idx, float4 v) {
+  if (KIND == 1) {
+    *reinterpret_cast<uint4*>(reinterpret_cast<float*>(base) + idx) = make_uint4(tc::to_tf32(v.x), tc::to_tf32(v.y), tc::to_tf32(v.z), tc::to_tf32(v.w));
+  } else {
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = make_uint2(tc::pack_bf16(v.x, v.y), tc::pack_bf16(v.z, v.w));
+  }
+}
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p, const int spc) {
+  extern __shared__ __align__(16) float sm[];
+  const int C = p.c0 + p.c1, L = p.L, LC = L * C, cpg = C / p.groups;
+  float* data = sm;                                   // [spc][LC]
+  float2* stats = reinterpret_cast<float2*>(sm + (size_t)spc * LC);  // [spc][groups]
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int b_first = blockIdx.x * spc;
+  const int nb = min(spc, p.B - b_first);
+  const int c4n = C >> 2;
+  // ---- load (coalesced float4), concat + skip scale applied here
+  for (int i = tid; i < nb * L * c4n; i += nthr) {
+    const int c = (i % c4n) * 4;
+    const int row = i / c4n;                 // local row: s * L + l
+    const size_t grow = (size_t)b_first * L + row;
+    float4 v;
+    if (c < p.c0) v = __ldg(reinterpret_cast<const float4*>(p.src0 + grow * p.c0 + c));
+    else {
+      v = __ldg(reinterpret_cast<const float4*>(p.src1 + grow * p.c1 + (c - p.c0)));
+      v.x *= p.scale1; v.y *= p.scale1; v.z *= p.scale1; v.w *= p.scale1;
+    }
+    *reinterpret_cast<float4*>(data + (size_t)row * C + c) = v;
+  }
+  __syncthreads();
+  // ---- two-pass statistics per (sample, group): one warp each
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  const int n = cpg * L;
+  for (int sg = warp; sg < nb * p.groups; sg += nwarps) {
+    const int s = sg / p.groups, g = sg - s * p.groups;
+    const float* base = data + (size_t)s * LC + g * cpg;
+    float sum = 0.f;
+    for (int i = lane; i < n; i += 32) { const int l = i / cpg; sum += base[l * C + (i - l * cpg)]; }
+    const float mean = warp_sum_f(sum) / (float)n;
+    float sq = 0.f;
+    for (int i = lane; i < n; i += 32) { const int l = i / cpg; const float d = base[l * C + (i - l * cpg)] - mean; sq = fmaf(d, d, sq); }
+    const float var = warp_sum_f(sq) / (float)n;
+    if (lane == 0) stats[sg] = make_float2(mean, 1.0f / sqrtf(var + p.eps));
+  }
+  __syncthreads();
+  // ---- apply
+  const float* aff = nullptr;
+  if (p.aff) aff = p.aff + (size_t)(p.call_idx ? *p.call_idx : 0) * p.aff_call_stride;
+  for (int i = tid; i < nb * L * c4n; i += nthr) {
+    const int c = (i % c4n) * 4;
+    const int row = i / c4n;
+    const int s = row / L;
+    const size_t gidx = ((size_t)b_first * L + row) * C + c;
+    float4 v = *reinterpret_cast<const float4*>(data + (size_t)row * C + c);
+    if (p.raw) store_op4<KIND>(p.raw, gidx, v);
+    const float2 st = stats[s * p.groups + c / cpg];
+    v.x = (v.x - st.x) * st.y; v.y = (v.y - st.x) * st.y; v.z = (v.z - st.x) * st.y; v.w = (v.w - st.x) * st.y;
+    if (aff) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(aff + c));
+      const float4 h = __ldg(reinterpret_cast<const float4*>(aff + C + c));
+      v.x = v.x * g.x + h.x; v.y = v.y * g.y + h.y; v.z = v.z * g.z + h.z; v.w = v.w * g.w + h.w;
+    }
+    if (p.silu) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+    store_op4<KIND>(p.out, gidx, v);
+  }
+}
+
+static int gn_spc(int L, int C) {
+  int spc = 4096 / (L * C);
+  if (spc < 1) spc = 1;
+  if (spc > 8) spc = 8;
+  return spc;
+}
+
+bool gn_apply_supported(int L, int C, int groups) {
+  if (C % 4 || C % groups || (C / groups) % 4) return false;
+  const size_t bytes = ((size_t)gn_spc(L, C) * L * C + 2 * 8 * 32) * sizeof(float);
+  return bytes <= 200 * 1024;
+}
+
+cudaError_t launch_gn_apply(const GnApplyParams& p, int kind, cudaStream_t s) {
+  if (p.B <= 0) return cudaSuccess;
+  const int C = p.c0 + p.c1;
+  const int spc = gn_spc(p.L, C);
+  const size_t smem = ((size_t)spc * p.L * C + 2 * (size_t)spc * p.groups) * sizeof(float);
+  const unsigned grid = (unsigned)((p.B + spc - 1) / spc);
+  if (kind == 1) gn_apply_kernel<1><<<grid, 256, smem, s>>>(p, spc);
+  else gn_apply_kernel<2><<<grid, 256, smem, s>>>(p, spc);
+  return cudaGetLastError();
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) ln_apply_kernel(const LnApplyParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= p.rows) return;
+  const int C = p.C;
+  const float* src = p.src + (size_t)row * C;
+  float4 v[8];  // C <= 1024
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = i * 128 + lane * 4;
+    if (c < C) { v[i] = __ldg(reinterpret_cast<const float4*>(src + c)); sum += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+  }
+  const float mean = warp_sum_f(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = i * 128 + lane * 4;
+    if (c < C) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      sq = fmaf(a, a, sq); sq = fmaf(b, b, sq); sq = fmaf(cc, cc, sq); sq = fmaf(d, d, sq);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum_f(sq) / (float)C + p.eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = i * 128 + lane * 4;
+    if (c < C) {
+      float4 o = make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd);
+      store_op4<KIND>(p.out, (size_t)row * C + c, o);
+    }
+  }
+}
+
+cudaError_t launch_ln_apply(const LnApplyParams& p, int kind, cudaStream_t s) {
+  if (p.rows <= 0) return cudaSuccess;
+  if (p.C % 4 || p.C > 1024) return cudaErrorInvalidValue;
+  const unsigned grid = (unsigned)((p.rows + 7) / 8);
+  if (kind == 1) ln_apply_kernel<1><<<grid, 256, 0, s>>>(p);
+  else ln_apply_kernel<2><<<grid, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t init_prep() {
+  cudaError_t e = cudaFuncSetAttribute(gn_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gn_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+}  // namespace mdt
