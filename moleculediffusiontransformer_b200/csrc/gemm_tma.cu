@@ -9,7 +9,7 @@
 //   warp 1     one lane issues tcgen05.mma (accumulator in TMEM), tcgen05.commit frees stages; owns TMEM
 //   warps 2-5  epilogue: tcgen05.ld -> smem staging -> coalesced bias / GELU / residual, fp32 and/or
 //              operand-dtype stores
-// 3 stages x 32 KB -> two CTAs per SM: one tile's epilogue overlaps the other's main loop.
+// Persistent, one CTA per SM: 5-stage smem ring, two TMEM accumulators so the epilogue of tile i overlaps tile i+1.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "aload.cuh"
@@ -19,33 +19,46 @@ namespace mdt {
 namespace tc {
 
 constexpr int T_TM = 128;
-constexpr int T_STAGES = 3;
+constexpr int T_STAGES = 5;
 constexpr int T_A_BYTES = T_TM * 128;
 constexpr int T_B_BYTES = 128 * 128;
 constexpr int T_STAGE_BYTES = T_A_BYTES + T_B_BYTES;
-constexpr int T_SMEM_BYTES = T_STAGES * T_STAGE_BYTES + 1024;
+constexpr int T_EPI_WARPS = 8;
+constexpr int T_STG_LD = 36;                                  // 32 columns + 4 floats of padding per staged row
+constexpr int T_STG_BYTES = T_EPI_WARPS * 32 * T_STG_LD * 4;  // per-warp private staging, 4.5 KB each
+constexpr int T_SMEM_BYTES = T_STAGES * T_STAGE_BYTES + T_STG_BYTES + 1024;
+constexpr int T_THREADS = 64 + 32 * T_EPI_WARPS;
 
+// Persistent kernel: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... with the N tile index
+// fastest, so concurrently running CTAs share A tiles (and the whole weight matrix) in L2.  Three pipelines:
+//   smem ring  (TMA producer  <-> MMA issuer)        full_bar / empty_bar       [T_STAGES]
+//   TMEM ring  (MMA issuer    <-> epilogue warps)    acc_full / acc_empty       [2 accumulators of BN columns]
+//   tile loop  (all roles derive the same tile sequence from blockIdx / gridDim)
 template <int KIND>
-__global__ void __launch_bounds__(192) gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                       const __grid_constant__ CUtensorMap tmB, const TmaGemmParams p,
-                                                       const uint32_t idesc) {
+__global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const TmaGemmParams p, const uint32_t idesc) {
   constexpr int KCH = (KIND == 1) ? 32 : 64;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[T_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[T_STAGES];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = p.BN;
-  const int m0 = blockIdx.x * T_TM, n0 = blockIdx.y * BN;
-  const uint32_t tmem_cols = BN <= 32 ? 32u : (BN <= 64 ? 64u : 128u);
+  const int n_tiles = p.N / BN;
+  const int m_tiles = (p.M + T_TM - 1) / T_TM;
+  const int total_tiles = m_tiles * n_tiles;
   const int num_chunks = p.taps * p.kchunks;
+  // two accumulators; narrow tiles still read 32 columns per tcgen05.ld, so keep 32 columns of slack
+  const uint32_t tmem_cols = BN <= 32 ? 64u : (BN <= 64 ? 128u : 256u);
 
   if (tid == 0) {
     for (int s = 0; s < T_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&accum_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], T_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
@@ -58,86 +71,112 @@ __global__ void __launch_bounds__(192) gemm_tma_kernel(const __grid_constant__ C
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int b0, l0;
-      if (p.L >= T_TM) { const int tps = p.L / T_TM; b0 = blockIdx.x / tps; l0 = (blockIdx.x - b0 * tps) * T_TM; }
-      else { b0 = blockIdx.x * p.Sb; l0 = 0; }
       const uint32_t tx = (uint32_t)(T_A_BYTES + BN * 128);
       int c = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        for (int kc = 0; kc < p.kchunks; ++kc, ++c) {
-          const int stage = c % T_STAGES;
-          const uint32_t phase = (uint32_t)(c / T_STAGES) & 1u;
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sa = smem + stage * T_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], tx);
-          tma_load_3d(sa, &tmA, &full_bar[stage], kc * KCH, l0 + tap - p.pad, b0);
-          tma_load_2d(sa + T_A_BYTES, &tmB, &full_bar[stage], tap * p.C + kc * KCH, n0);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int mt = t / n_tiles, nt = t - mt * n_tiles;
+        int b0, l0;
+        if (p.L >= T_TM) { const int tps = p.L / T_TM; b0 = mt / tps; l0 = (mt - b0 * tps) * T_TM; }
+        else { b0 = mt * p.Sb; l0 = 0; }
+        for (int tap = 0; tap < p.taps; ++tap) {
+          for (int kc = 0; kc < p.kchunks; ++kc, ++c) {
+            const int stage = c % T_STAGES;
+            const uint32_t phase = (uint32_t)(c / T_STAGES) & 1u;
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sa = smem + stage * T_STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], tx);
+            tma_load_3d(sa, &tmA, &full_bar[stage], kc * KCH, l0 + tap - p.pad, b0);
+            tma_load_2d(sa + T_A_BYTES, &tmB, &full_bar[stage], tap * p.C + kc * KCH, nt * BN);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    for (int c = 0; c < num_chunks; ++c) {
-      const int stage = c % T_STAGES;
-      const uint32_t phase = (uint32_t)(c / T_STAGES) & 1u;
-      mbar_wait(&full_bar[stage], phase);
+    int c = 0, it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&acc_empty[buf], aphase ^ 1u);      // epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + stage * T_STAGE_BYTES);
-        const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + T_A_BYTES);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+      for (int k0 = 0; k0 < num_chunks; ++k0, ++c) {
+        const int stage = c % T_STAGES;
+        const uint32_t phase = (uint32_t)(c / T_STAGES) & 1u;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * T_STAGE_BYTES);
+          const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + T_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma<KIND>(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((c | k) != 0));
-        umma_commit(&empty_bar[stage]);
-        if (c == num_chunks - 1) umma_commit(&accum_bar);
+          for (int k = 0; k < 4; ++k)
+            umma<KIND>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((k0 | k) != 0));
+          umma_commit(&empty_bar[stage]);
+          if (k0 == num_chunks - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;            // TMEM lane quadrant this warp may access
-    const int r = q * 32 + lane;       // tile row owned for the TMEM -> smem transfer
-    const int et = (warp - 2) * 32 + lane;
-    mbar_wait(&accum_bar, 0u);
-    tc_fence_after();
-    float* stg = reinterpret_cast<float*>(smem);
-    const int ldst = BN + 4;
-    for (int cc = 0; cc * 32 < BN; ++cc) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
-      const int ncol = min(32, BN - cc * 32);
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int ew = warp - 2;             // 0..7
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;            // column half handled by this warp
+    float* stg = reinterpret_cast<float*>(smem + T_STAGES * T_STAGE_BYTES) + (size_t)ew * 32 * T_STG_LD;
+    const int cols_per_half = BN >= 64 ? BN / 2 : BN;   // narrow tiles: only the first four warps work
+    const bool active = BN >= 64 || half == 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int mt = t / n_tiles, nt = t - mt * n_tiles;
+      const int buf = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&acc_full[buf], aphase);
+      tc_fence_after();
+      if (active) {
+        const int col0 = half * cols_per_half;
+        for (int cc = 0; cc < cols_per_half; cc += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0 + cc), v);
+          const int ncol = min(32, cols_per_half - cc);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j * 4 < ncol)
-          *reinterpret_cast<uint4*>(stg + (size_t)r * ldst + cc * 32 + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
-    tc_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const int n4 = BN >> 2;
-    for (int idx = et; idx < T_TM * n4; idx += 128) {
-      const int rr = idx / n4, c4 = (idx - rr * n4) * 4;
-      const int mo = m0 + rr, no = n0 + c4;
-      if (mo >= p.M || no >= p.N) continue;
-      float4 o = *reinterpret_cast<const float4*>(stg + (size_t)rr * ldst + c4);
-      if (p.bias) {
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + no));
-        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-      }
-      if (p.act == 1) { o.x = gelu_f(o.x); o.y = gelu_f(o.y); o.z = gelu_f(o.z); o.w = gelu_f(o.w); }
-      if (p.res) {
-        const float4 rv = *reinterpret_cast<const float4*>(p.res + (size_t)mo * p.ldres + no);
-        o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-      }
-      if (p.C32) *reinterpret_cast<float4*>(p.C32 + (size_t)mo * p.ldc + no) = o;
-      if (p.Cop) {
-        if (KIND == 1) {
-          *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.Cop) + (size_t)mo * p.ldcop + no) =
-              make_uint4(to_tf32(o.x), to_tf32(o.y), to_tf32(o.z), to_tf32(o.w));
-        } else {
-          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.Cop) + (size_t)mo * p.ldcop + no) =
-              make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * T_STG_LD + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          // coalesced: 8 lanes cover one 128-byte row segment, 4 rows per pass
+          const int cl = (lane & 7) * 4;
+#pragma unroll
+          for (int rr = lane >> 3; rr < 32; rr += 4) {
+            const int mo = mt * T_TM + q * 32 + rr, no = nt * BN + col0 + cc + cl;
+            if (mo < p.M && cl < ncol) {
+              float4 o = *reinterpret_cast<const float4*>(stg + rr * T_STG_LD + cl);
+              if (p.bias) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + no));
+                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+              }
+              if (p.act == 1) { o.x = gelu_f(o.x); o.y = gelu_f(o.y); o.z = gelu_f(o.z); o.w = gelu_f(o.w); }
+              if (p.res) {
+                const float4 rv = *reinterpret_cast<const float4*>(p.res + (size_t)mo * p.ldres + no);
+                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+              }
+              if (p.C32) *reinterpret_cast<float4*>(p.C32 + (size_t)mo * p.ldc + no) = o;
+              if (p.Cop) {
+                if (KIND == 1) {
+                  *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.Cop) + (size_t)mo * p.ldcop + no) =
+                      make_uint4(to_tf32(o.x), to_tf32(o.y), to_tf32(o.z), to_tf32(o.w));
+                } else {
+                  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.Cop) + (size_t)mo * p.ldcop + no) =
+                      make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+                }
+              }
+            }
+          }
+          __syncwarp();
         }
       }
+      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld inside tmem_ld32): hand it back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   }
   tc_fence_before();
@@ -213,16 +252,25 @@ cudaError_t init_gemm_tma() {
   return cudaFuncSetAttribute(tc::gemm_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::T_SMEM_BYTES);
 }
 
+static int g_num_sms = 0;
+
 cudaError_t launch_gemm_tma(const void* tmA, const void* tmB, const TmaGemmParams& p, int kind, cudaStream_t s) {
   if (p.M <= 0 || p.N <= 0) return cudaSuccess;
   if (p.BN <= 0 || p.N % p.BN) return cudaErrorInvalidValue;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
   const uint32_t fmt = kind == 1 ? 2u : 1u;
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(tc::T_TM >> 4) << 24);
-  dim3 grid((p.M + tc::T_TM - 1) / tc::T_TM, p.N / p.BN);
+  const long long tiles = (long long)((p.M + tc::T_TM - 1) / tc::T_TM) * (p.N / p.BN);
+  const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);   // persistent: one CTA per SM
   const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(tmA);
   const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(tmB);
-  if (kind == 1) tc::gemm_tma_kernel<1><<<grid, 192, tc::T_SMEM_BYTES, s>>>(a, b, p, idesc);
-  else tc::gemm_tma_kernel<2><<<grid, 192, tc::T_SMEM_BYTES, s>>>(a, b, p, idesc);
+  if (kind == 1) tc::gemm_tma_kernel<1><<<grid, tc::T_THREADS, tc::T_SMEM_BYTES, s>>>(a, b, p, idesc);
+  else tc::gemm_tma_kernel<2><<<grid, tc::T_THREADS, tc::T_SMEM_BYTES, s>>>(a, b, p, idesc);
   return cudaGetLastError();
 }
 

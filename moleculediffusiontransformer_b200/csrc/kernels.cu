@@ -238,17 +238,34 @@ __global__ void attention_kernel(const AttnParams p, int warps_per_cta) {
     *reinterpret_cast<float4*>(vs + r * d + c) = IO::ld4(vbase, koff + (size_t)r * p.ldkv + h * d + c);
   }
   __syncwarp();
-  // S = (Q K^T) * scale
-  for (int pair = lane; pair < nq * nk; pair += 32) {
-    const int i = pair / nk, j = pair - i * nk;
-    const float4* qi = reinterpret_cast<const float4*>(qs + i * dp);
-    const float4* kj = reinterpret_cast<const float4*>(ks + j * dp);
-    float acc = 0.f;
-    for (int c = 0; c < d4; ++c) {
-      const float4 x = qi[c], y = kj[c];
-      acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+  // S = (Q K^T) * scale : 2 x 4 register tiles (6 shared loads per 32 FMAs)
+  {
+    const int nbi = (nq + 1) >> 1, nbj = (nk + 3) >> 2;
+    for (int blk = lane; blk < nbi * nbj; blk += 32) {
+      const int i0 = (blk / nbj) * 2, j0 = (blk % nbj) * 4;
+      const int i1 = min(i0 + 1, nq - 1);
+      const int jj[4] = {j0, min(j0 + 1, nk - 1), min(j0 + 2, nk - 1), min(j0 + 3, nk - 1)};
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      for (int c = 0; c < d4; ++c) {
+        const float4 qa = *reinterpret_cast<const float4*>(qs + i0 * dp + c * 4);
+        const float4 qb = *reinterpret_cast<const float4*>(qs + i1 * dp + c * 4);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float4 kk = *reinterpret_cast<const float4*>(ks + jj[t] * dp + c * 4);
+          acc[0][t] = fmaf(qa.x, kk.x, acc[0][t]); acc[0][t] = fmaf(qa.y, kk.y, acc[0][t]);
+          acc[0][t] = fmaf(qa.z, kk.z, acc[0][t]); acc[0][t] = fmaf(qa.w, kk.w, acc[0][t]);
+          acc[1][t] = fmaf(qb.x, kk.x, acc[1][t]); acc[1][t] = fmaf(qb.y, kk.y, acc[1][t]);
+          acc[1][t] = fmaf(qb.z, kk.z, acc[1][t]); acc[1][t] = fmaf(qb.w, kk.w, acc[1][t]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (j0 + t < nk) {
+          ss[i0 * (nk + 1) + j0 + t] = acc[0][t] * p.scale;
+          if (i0 + 1 < nq) ss[(i0 + 1) * (nk + 1) + j0 + t] = acc[1][t] * p.scale;
+        }
+      }
     }
-    ss[i * (nk + 1) + j] = acc * p.scale;
   }
   __syncwarp();
   // row softmax
@@ -262,13 +279,50 @@ __global__ void attention_kernel(const AttnParams p, int warps_per_cta) {
     for (int j = 0; j < nk; ++j) row[j] *= inv;
   }
   __syncwarp();
-  // O = P V
-  for (int dd = lane; dd < d; dd += 32) {
-    for (int i = 0; i < nq; ++i) {
-      const float* row = ss + i * (nk + 1);
-      float acc = 0.f;
-      for (int j = 0; j < nk; ++j) acc = fmaf(row[j], vs[j * d + dd], acc);
-      IO::st(p.o, ((size_t)b * nq + i) * p.ldo + h * d + dd, acc);
+  // O = P V : each lane owns DD = d / 32 output features; V chunk (16 keys) and 16 query rows live in registers
+  if (d == 64) {
+    for (int i0 = 0; i0 < nq; i0 += 16) {
+      float acc[16][2];
+#pragma unroll
+      for (int ii = 0; ii < 16; ++ii) { acc[ii][0] = 0.f; acc[ii][1] = 0.f; }
+      for (int j0 = 0; j0 < nk; j0 += 16) {
+        float vr[16][2];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const bool ok = j0 + t < nk;
+          vr[t][0] = ok ? vs[(j0 + t) * d + lane] : 0.f;
+          vr[t][1] = ok ? vs[(j0 + t) * d + 32 + lane] : 0.f;
+        }
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) {
+          if (i0 + ii < nq) {
+            const float* row = ss + (i0 + ii) * (nk + 1) + j0;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const float pv = (j0 + t < nk) ? row[t] : 0.f;
+              acc[ii][0] = fmaf(pv, vr[t][0], acc[ii][0]);
+              acc[ii][1] = fmaf(pv, vr[t][1], acc[ii][1]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int ii = 0; ii < 16; ++ii) {
+        if (i0 + ii < nq) {
+          const size_t o = ((size_t)b * nq + i0 + ii) * p.ldo + h * d;
+          IO::st(p.o, o + lane, acc[ii][0]);
+          IO::st(p.o, o + 32 + lane, acc[ii][1]);
+        }
+      }
+    }
+  } else {
+    for (int dd = lane; dd < d; dd += 32) {
+      for (int i = 0; i < nq; ++i) {
+        const float* row = ss + i * (nk + 1);
+        float acc = 0.f;
+        for (int j = 0; j < nk; ++j) acc = fmaf(row[j], vs[j * d + dd], acc);
+        IO::st(p.o, ((size_t)b * nq + i) * p.ldo + h * d + dd, acc);
+      }
     }
   }
 }
@@ -279,11 +333,13 @@ cudaError_t init_kernels() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = init_prep();
+  if (e == cudaSuccess) e = init_attention_bulk();
   return e;
 }
 
 cudaError_t launch_attention(const AttnParams& p, int kind, cudaStream_t s) {
   if (p.B <= 0) return cudaSuccess;
+  if (attention_bulk_supported(p, kind)) return launch_attention_bulk(p, kind, s);
   if (p.d % 4 != 0 || p.nq > 128 || p.nk > 128) return cudaErrorInvalidValue;
   const size_t per_warp = ((((size_t)(p.nq + p.nk) * (p.d + 4) + (size_t)p.nk * p.d + (size_t)p.nq * (p.nk + 1)) + 3) & ~(size_t)3) * sizeof(float);
   int wpc = (int)((96 * 1024) / per_warp);

@@ -105,6 +105,10 @@ cudaError_t init_gemm_tc();
 cudaError_t launch_gemm_fp32(const GemmParams& p, cudaStream_t s);
 // kind: 0 fp32 in/out, 1 fp32 in / tf32-rounded fp32 out, 2 bf16 in/out
 cudaError_t launch_attention(const AttnParams& p, int kind, cudaStream_t s);
+// TMA-bulk-copy streaming variant (attention_bulk.cu); launch_attention dispatches to it when the shape fits
+bool attention_bulk_supported(const AttnParams& p, int kind);
+cudaError_t init_attention_bulk();
+cudaError_t launch_attention_bulk(const AttnParams& p, int kind, cudaStream_t s);
 cudaError_t launch_groupnorm_stats(const NormStatsParams& p, cudaStream_t s);
 cudaError_t launch_rownorm_stats(const NormStatsParams& p, cudaStream_t s);
 // out[b, o, co] = bias[co] + sum_j Y[b, i_j, k_j * Cout + co] (+ add[b, o, co]);  ConvTranspose1d(k=2f, s=f, p=f/2)

@@ -48,21 +48,52 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p, co
     *reinterpret_cast<float4*>(data + (size_t)row * C + c) = v;
   }
   __syncthreads();
-  // ---- two-pass statistics per (sample, group): one warp each
+  // ---- two-pass statistics per (sample, group)
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
   const int n = cpg * L;
-  for (int sg = warp; sg < nb * p.groups; sg += nwarps) {
-    const int s = sg / p.groups, g = sg - s * p.groups;
+  const int ngroups = nb * p.groups;
+  if (ngroups >= nwarps) {
+    // one warp per (sample, group)
+    for (int sg = warp; sg < ngroups; sg += nwarps) {
+      const int s = sg / p.groups, g = sg - s * p.groups;
+      const float* base = data + (size_t)s * LC + g * cpg;
+      float sum = 0.f;
+      for (int i = lane; i < n; i += 32) { const int l = i / cpg; sum += base[l * C + (i - l * cpg)]; }
+      const float mean = warp_sum_f(sum) / (float)n;
+      float sq = 0.f;
+      for (int i = lane; i < n; i += 32) { const int l = i / cpg; const float d = base[l * C + (i - l * cpg)] - mean; sq = fmaf(d, d, sq); }
+      const float var = warp_sum_f(sq) / (float)n;
+      if (lane == 0) stats[sg] = make_float2(mean, 1.0f / sqrtf(var + p.eps));
+    }
+    __syncthreads();
+  } else {
+    // few large groups (Patcher / Unpatcher GroupNorm(1)): split every group over wpg warps
+    __shared__ float part[8];
+    const int wpg = nwarps / ngroups;
+    const int sg = warp / wpg, sub = warp - sg * wpg;
+    const bool on = sg < ngroups;
+    const int s = on ? sg / p.groups : 0, g = on ? sg - s * p.groups : 0;
     const float* base = data + (size_t)s * LC + g * cpg;
     float sum = 0.f;
-    for (int i = lane; i < n; i += 32) { const int l = i / cpg; sum += base[l * C + (i - l * cpg)]; }
-    const float mean = warp_sum_f(sum) / (float)n;
+    if (on) for (int i = sub * 32 + lane; i < n; i += wpg * 32) { const int l = i / cpg; sum += base[l * C + (i - l * cpg)]; }
+    sum = warp_sum_f(sum);
+    if (lane == 0) part[warp] = sum;
+    __syncthreads();
+    float mean = 0.f;
+    if (on) { for (int w = 0; w < wpg; ++w) mean += part[sg * wpg + w]; mean /= (float)n; }
+    __syncthreads();
     float sq = 0.f;
-    for (int i = lane; i < n; i += 32) { const int l = i / cpg; const float d = base[l * C + (i - l * cpg)] - mean; sq = fmaf(d, d, sq); }
-    const float var = warp_sum_f(sq) / (float)n;
-    if (lane == 0) stats[sg] = make_float2(mean, 1.0f / sqrtf(var + p.eps));
+    if (on) for (int i = sub * 32 + lane; i < n; i += wpg * 32) { const int l = i / cpg; const float d = base[l * C + (i - l * cpg)] - mean; sq = fmaf(d, d, sq); }
+    sq = warp_sum_f(sq);
+    if (lane == 0) part[warp] = sq;
+    __syncthreads();
+    if (on && sub == 0 && lane == 0) {
+      float var = 0.f;
+      for (int w = 0; w < wpg; ++w) var += part[sg * wpg + w];
+      stats[sg] = make_float2(mean, 1.0f / sqrtf(var / (float)n + p.eps));
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // ---- apply
   const float* aff = nullptr;
   if (p.aff) aff = p.aff + (size_t)(p.call_idx ? *p.call_idx : 0) * p.aff_call_stride;
