@@ -7,8 +7,7 @@
 // buffer i & 1 the copies of item i + 1 are in flight.  Each warp owns one (sample, head) pair at a time:
 // S = Q K^T in 2 x 4 register tiles, softmax, O = P V with V and the accumulators in registers.
 #include <cuda_bf16.h>
-#include "kernels.cuh"
-#include "tc_common.cuh"
+#include "attn_math.cuh"
 
 namespace mdt {
 
@@ -19,221 +18,10 @@ struct BulkAttnCfg {
   int groups, hchunks;  // work decomposition
 };
 
-template <int KIND> struct SmemIO;
-template <> struct SmemIO<0> {
-  typedef float T;
-  static __device__ __forceinline__ float4 ld4(const T* p) { return *reinterpret_cast<const float4*>(p); }
-  static __device__ __forceinline__ float ld1(const T* p) { return *p; }
-  static __device__ __forceinline__ void st(void* o, size_t i, float v) { reinterpret_cast<float*>(o)[i] = v; }
-};
-template <> struct SmemIO<1> {
-  typedef float T;
-  static __device__ __forceinline__ float4 ld4(const T* p) { return *reinterpret_cast<const float4*>(p); }
-  static __device__ __forceinline__ float ld1(const T* p) { return *p; }
-  static __device__ __forceinline__ void st(void* o, size_t i, float v) { reinterpret_cast<uint32_t*>(o)[i] = tc::to_tf32(v); }
-};
-template <> struct SmemIO<2> {
-  typedef __nv_bfloat16 T;
-  static __device__ __forceinline__ float4 ld4(const T* p) {
-    const uint2 u = *reinterpret_cast<const uint2*>(p);
-    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-    return make_float4(a.x, a.y, b.x, b.y);
-  }
-  static __device__ __forceinline__ float ld1(const T* p) { return __bfloat162float(*p); }
-  static __device__ __forceinline__ void st(void* o, size_t i, float v) { reinterpret_cast<__nv_bfloat16*>(o)[i] = __float2bfloat16_rn(v); }
-};
-
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(tc::smem_u32(bar))
                : "memory");
-}
-
-// One (sample, head): q rows at qs (stride sa), k rows at ks and v rows at vs (stride sb); ss = nq x (nk + 1) scratch.
-template <int KIND>
-__device__ __forceinline__ void attend_head(const typename SmemIO<KIND>::T* qs, int sa, const typename SmemIO<KIND>::T* ks,
-                                            const typename SmemIO<KIND>::T* vs, int sb, float* ss, int nq, int nk, int d,
-                                            float scale, void* out, size_t out_base, int ldo, int lane) {
-  typedef SmemIO<KIND> IO;
-  const int d4 = d >> 2;
-  const int nbi = (nq + 1) >> 1, nbj = (nk + 3) >> 2;
-  for (int blk = lane; blk < nbi * nbj; blk += 32) {
-    const int i0 = (blk / nbj) * 2, j0 = (blk % nbj) * 4;
-    const int i1 = min(i0 + 1, nq - 1);
-    const int jj[4] = {j0, min(j0 + 1, nk - 1), min(j0 + 2, nk - 1), min(j0 + 3, nk - 1)};
-    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    for (int c = 0; c < d4; ++c) {
-      const float4 qa = IO::ld4(qs + i0 * sa + c * 4);
-      const float4 qb = IO::ld4(qs + i1 * sa + c * 4);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float4 kk = IO::ld4(ks + jj[t] * sb + c * 4);
-        acc[0][t] = fmaf(qa.x, kk.x, acc[0][t]); acc[0][t] = fmaf(qa.y, kk.y, acc[0][t]);
-        acc[0][t] = fmaf(qa.z, kk.z, acc[0][t]); acc[0][t] = fmaf(qa.w, kk.w, acc[0][t]);
-        acc[1][t] = fmaf(qb.x, kk.x, acc[1][t]); acc[1][t] = fmaf(qb.y, kk.y, acc[1][t]);
-        acc[1][t] = fmaf(qb.z, kk.z, acc[1][t]); acc[1][t] = fmaf(qb.w, kk.w, acc[1][t]);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (j0 + t < nk) {
-        ss[i0 * (nk + 1) + j0 + t] = acc[0][t] * scale;
-        if (i0 + 1 < nq) ss[(i0 + 1) * (nk + 1) + j0 + t] = acc[1][t] * scale;
-      }
-    }
-  }
-  __syncwarp();
-  for (int i = lane; i < nq; i += 32) {
-    float* row = ss + i * (nk + 1);
-    float mx = row[0];
-    for (int j = 1; j < nk; ++j) mx = fmaxf(mx, row[j]);
-    float sum = 0.f;
-    for (int j = 0; j < nk; ++j) { const float e = expf(row[j] - mx); row[j] = e; sum += e; }
-    const float inv = 1.0f / sum;
-    for (int j = 0; j < nk; ++j) row[j] *= inv;
-  }
-  __syncwarp();
-  // O = P V, d == 64: lane owns features lane and lane + 32; 8 query rows x 16 keys per register tile
-  for (int i0 = 0; i0 < nq; i0 += 8) {
-    float acc[8][2];
-#pragma unroll
-    for (int ii = 0; ii < 8; ++ii) { acc[ii][0] = 0.f; acc[ii][1] = 0.f; }
-    for (int j0 = 0; j0 < nk; j0 += 16) {
-      float vr[16][2];
-#pragma unroll
-      for (int t = 0; t < 16; ++t) {
-        const bool ok = j0 + t < nk;
-        vr[t][0] = ok ? IO::ld1(vs + (j0 + t) * sb + lane) : 0.f;
-        vr[t][1] = ok ? IO::ld1(vs + (j0 + t) * sb + 32 + lane) : 0.f;
-      }
-#pragma unroll
-      for (int ii = 0; ii < 8; ++ii) {
-        if (i0 + ii < nq) {
-          const float* row = ss + (i0 + ii) * (nk + 1) + j0;
-#pragma unroll
-          for (int t = 0; t < 16; ++t) {
-            const float pv = (j0 + t < nk) ? row[t] : 0.f;
-            acc[ii][0] = fmaf(pv, vr[t][0], acc[ii][0]);
-            acc[ii][1] = fmaf(pv, vr[t][1], acc[ii][1]);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int ii = 0; ii < 8; ++ii) {
-      if (i0 + ii < nq) {
-        const size_t o = out_base + (size_t)(i0 + ii) * ldo;
-        IO::st(out, o + lane, acc[ii][0]);
-        IO::st(out, o + 32 + lane, acc[ii][1]);
-      }
-    }
-  }
-  __syncwarp();
-}
-
-// ---- warp-level tensor-core variant for the tensor-core precisions (operands are already tf32 / bf16 values) ----
-// S = Q K^T and O = P V with mma.sync.m16n8k8 (tf32 inputs, fp32 accumulate).  The row padding of 4 floats makes
-// every fragment load hit 32 distinct banks.  P (C-fragment layout) feeds the second MMA as an A fragment by
-// permuting the key index consistently on both operands (column q <-> key 8t + 2q, column q + 4 <-> key 8t + 2q + 1).
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-template <int KIND>
-__device__ __forceinline__ void attend_head_mma(const typename SmemIO<KIND>::T* qs, int sa, const typename SmemIO<KIND>::T* ks,
-                                                const typename SmemIO<KIND>::T* vs, int sb, int nq, int nk, float scale, void* out,
-                                                size_t out_base, int ldo, int lane) {
-  typedef SmemIO<KIND> IO;
-  constexpr int MAXNT = 8;                       // nk <= 64
-  const int nt = (nk + 7) >> 3;
-  const int g = lane >> 2, q = lane & 3;
-  for (int i0 = 0; i0 < nq; i0 += 16) {
-    const int r0 = min(i0 + g, nq - 1), r1 = min(i0 + g + 8, nq - 1);
-    float sc[MAXNT][4];
-#pragma unroll
-    for (int t = 0; t < MAXNT; ++t) { sc[t][0] = 0.f; sc[t][1] = 0.f; sc[t][2] = 0.f; sc[t][3] = 0.f; }
-#pragma unroll
-    for (int k0 = 0; k0 < 64; k0 += 8) {
-      uint32_t a[4];
-      a[0] = __float_as_uint(IO::ld1(qs + r0 * sa + k0 + q));
-      a[1] = __float_as_uint(IO::ld1(qs + r1 * sa + k0 + q));
-      a[2] = __float_as_uint(IO::ld1(qs + r0 * sa + k0 + q + 4));
-      a[3] = __float_as_uint(IO::ld1(qs + r1 * sa + k0 + q + 4));
-#pragma unroll
-      for (int t = 0; t < MAXNT; ++t) {
-        if (t < nt) {
-          const int j = min(t * 8 + g, nk - 1);
-          const uint32_t b0 = __float_as_uint(IO::ld1(ks + j * sb + k0 + q));
-          const uint32_t b1 = __float_as_uint(IO::ld1(ks + j * sb + k0 + q + 4));
-          mma_tf32_16x8x8(sc[t], a, b0, b1);
-        }
-      }
-    }
-    // softmax over keys: thread holds columns 8t + 2q, 8t + 2q + 1 of rows g (c0, c1) and g + 8 (c2, c3)
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int t = 0; t < MAXNT; ++t) {
-      if (t < nt) {
-        const int j = t * 8 + 2 * q;
-        sc[t][0] = (j < nk) ? sc[t][0] * scale : -INFINITY;
-        sc[t][1] = (j + 1 < nk) ? sc[t][1] * scale : -INFINITY;
-        sc[t][2] = (j < nk) ? sc[t][2] * scale : -INFINITY;
-        sc[t][3] = (j + 1 < nk) ? sc[t][3] * scale : -INFINITY;
-        m0 = fmaxf(m0, fmaxf(sc[t][0], sc[t][1]));
-        m1 = fmaxf(m1, fmaxf(sc[t][2], sc[t][3]));
-      }
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int t = 0; t < MAXNT; ++t) {
-      if (t < nt) {
-        sc[t][0] = expf(sc[t][0] - m0); sc[t][1] = expf(sc[t][1] - m0);
-        sc[t][2] = expf(sc[t][2] - m1); sc[t][3] = expf(sc[t][3] - m1);
-        s0 += sc[t][0] + sc[t][1]; s1 += sc[t][2] + sc[t][3];
-      }
-    }
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-    const float inv0 = 1.0f / s0, inv1 = 1.0f / s1;
-    // O = P V : 8 feature tiles of 8, one k-step per key tile
-    float oc[8][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) { oc[n][0] = 0.f; oc[n][1] = 0.f; oc[n][2] = 0.f; oc[n][3] = 0.f; }
-#pragma unroll
-    for (int t = 0; t < MAXNT; ++t) {
-      if (t < nt) {
-        uint32_t a[4];
-        a[0] = tc::to_tf32(sc[t][0] * inv0);   // (row g,     key 8t + 2q)
-        a[1] = tc::to_tf32(sc[t][2] * inv1);   // (row g + 8, key 8t + 2q)
-        a[2] = tc::to_tf32(sc[t][1] * inv0);   // (row g,     key 8t + 2q + 1)
-        a[3] = tc::to_tf32(sc[t][3] * inv1);   // (row g + 8, key 8t + 2q + 1)
-        const int j0 = min(t * 8 + 2 * q, nk - 1), j1 = min(t * 8 + 2 * q + 1, nk - 1);   // masked keys carry p = 0
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-          const uint32_t b0 = __float_as_uint(IO::ld1(vs + j0 * sb + n * 8 + g));
-          const uint32_t b1 = __float_as_uint(IO::ld1(vs + j1 * sb + n * 8 + g));
-          mma_tf32_16x8x8(oc[n], a, b0, b1);
-        }
-      }
-    }
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const int col = n * 8 + 2 * q;
-      if (i0 + g < nq) {
-        const size_t o = out_base + (size_t)(i0 + g) * ldo + col;
-        IO::st(out, o, oc[n][0]); IO::st(out, o + 1, oc[n][1]);
-      }
-      if (i0 + g + 8 < nq) {
-        const size_t o = out_base + (size_t)(i0 + g + 8) * ldo + col;
-        IO::st(out, o, oc[n][2]); IO::st(out, o + 1, oc[n][3]);
-      }
-    }
-  }
 }
 
 template <int KIND>
@@ -297,7 +85,7 @@ __global__ void __launch_bounds__(256, 1) attention_bulk_kernel(const AttnParams
         attend_head<KIND>(A + (size_t)(s * nq) * c.strideA + hl * d, c.strideA, ks, ks + c.HC * d, c.strideB, ss, nq, nk, d, p.scale,
                           p.o, ob, p.ldo, lane);
       else
-        attend_head_mma<KIND>(A + (size_t)(s * nq) * c.strideA + hl * d, c.strideA, ks, ks + c.HC * d, c.strideB, nq, nk, p.scale,
+        attend_head_mma<KIND, KIND>(A + (size_t)(s * nq) * c.strideA + hl * d, c.strideA, ks, ks + c.HC * d, c.strideB, nq, nk, p.scale,
                               p.o, ob, p.ldo, lane);
     }
     __syncthreads();   // every warp is done with this stage buffer

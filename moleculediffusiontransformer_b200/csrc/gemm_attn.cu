@@ -1,0 +1,229 @@
+// gemm_attn.cu -- fused projection + attention for sm_100a: the per-head [q | k | v] projection runs on tcgen05
+// with the accumulator in TMEM and the attention core runs in the epilogue, so the (rows x 3 * heads * d) q/k/v
+// tensor never goes to HBM.
+//
+//   self  : tile = (128 rows, head h): D[128, 192] = LN(x)[128, C] * Wh[192, C]^T  (Wh = [Wq_h; Wk_h; Wv_h], LayerNorm
+//           affine folded), epilogue adds the folded bias, stages q / k / v per sample in shared memory and runs
+//           softmax(q k^T * scale) v per sample with mma.sync, writing only the (rows x d) head output.
+//   cross : D[128, 64] = LN(x) * Wq_h^T; K / V of the conditioning come from the loop-invariant per-sample cache.
+//
+// Persistent CTA per SM, same three pipelines as gemm_tma.cu (smem ring fed by TMA, two TMEM accumulators, tile loop
+// with the head index fastest so the eight heads of one row block share the activation tile in L2).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "attn_math.cuh"
+
+namespace mdt {
+namespace tc {
+
+constexpr int A_TM = 128;
+constexpr int A_STAGES = 2;
+constexpr int A_ABYTES = A_TM * 128;
+constexpr int A_EPI_WARPS = 8;
+constexpr int A_THREADS = 64 + 32 * A_EPI_WARPS;
+constexpr int A_LD = 68;   // staged q/k/v row stride in floats (64 + 4: conflict-free fragment loads)
+
+template <int KIND>
+__global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const GemmAttnParams p, const uint32_t idesc) {
+  constexpr int KCH = (KIND == 1) ? 32 : 64;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[A_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[A_STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int BN = p.cross ? p.d : 3 * p.d;
+  const int b_bytes = BN * 128;
+  const int stage_bytes = A_ABYTES + ((b_bytes + 1023) & ~1023);
+  const int m_tiles = (p.M + A_TM - 1) / A_TM;
+  const int total_tiles = m_tiles * p.heads;
+  const uint32_t tmem_cols = p.cross ? 128u : 512u;   // two accumulators of BN columns
+  float* Qs = reinterpret_cast<float*>(smem + A_STAGES * stage_bytes);
+  float* Ks = Qs + A_TM * A_LD;                       // self: staged k rows; cross: per-warp K scratch base
+  float* Vs = Ks + A_TM * A_LD;
+
+  if (tid == 0) {
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], A_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)(A_ABYTES + b_bytes);
+      int c = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int mt = t / p.heads, h = t - mt * p.heads;
+        for (int kc = 0; kc < p.kchunks; ++kc, ++c) {
+          const int stage = c % A_STAGES;
+          const uint32_t phase = (uint32_t)(c / A_STAGES) & 1u;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx);
+          tma_load_3d(sa, &tmA, &full_bar[stage], kc * KCH, 0, mt * p.Sb);
+          tma_load_2d(sa + A_ABYTES, &tmB, &full_bar[stage], kc * KCH, h * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    int c = 0, it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&acc_empty[buf], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+      for (int k0 = 0; k0 < p.kchunks; ++k0, ++c) {
+        const int stage = c % A_STAGES;
+        const uint32_t phase = (uint32_t)(c / A_STAGES) & 1u;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + A_ABYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma<KIND>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((k0 | k) != 0));
+          umma_commit(&empty_bar[stage]);
+          if (k0 == p.kchunks - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue + attention (warps 2..9)
+    const int ew = warp - 2;
+    const int q = warp & 3;                 // TMEM lane quadrant
+    const int half = ew >> 2;
+    const int row = q * 32 + lane;          // tile row owned for the TMEM -> smem transfer
+    const int cols_per_warp = BN / 2;       // 96 (self) or 32 (cross)
+    const int L = p.L;
+    // cross: warp-private K / V scratch [nk][A_LD] each, carved from the Ks region onwards
+    float* Kw = Ks + (size_t)ew * 2 * p.nk * A_LD;
+    float* Vw = Kw + (size_t)p.nk * A_LD;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int mt = t / p.heads, h = t - mt * p.heads;
+      const int m0 = mt * A_TM;
+      const int buf = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&acc_full[buf], aphase);
+      tc_fence_after();
+      for (int cc = 0; cc < cols_per_warp; cc += 32) {
+        uint32_t v[32];
+        const int col0 = half * cols_per_warp + cc;
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0), v);
+        float* dst = (col0 < 64 ? Qs : (col0 < 128 ? Ks : Vs)) + (size_t)row * A_LD + (col0 & 63);
+        const float* bias = p.bias + h * BN + col0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + j * 4));
+          *reinterpret_cast<uint4*>(dst + j * 4) =
+              make_uint4(to_tf32(__uint_as_float(v[4 * j]) + bv.x), to_tf32(__uint_as_float(v[4 * j + 1]) + bv.y),
+                         to_tf32(__uint_as_float(v[4 * j + 2]) + bv.z), to_tf32(__uint_as_float(v[4 * j + 3]) + bv.w));
+        }
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");           // q / k / v of the whole tile are staged
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);             // the accumulator may be overwritten now
+      for (int s = ew; s < p.Sb; s += A_EPI_WARPS) {
+        const int mrow = m0 + s * L;
+        if (mrow >= p.M) break;
+        const size_t ob = (size_t)mrow * p.ldo + (size_t)h * p.d;
+        if (!p.cross) {
+          attend_head_mma<1, KIND>(Qs + (size_t)s * L * A_LD, A_LD, Ks + (size_t)s * L * A_LD, Vs + (size_t)s * L * A_LD, A_LD, L, L,
+                                   p.scale, p.att, ob, p.ldo, lane);
+        } else {
+          const int b = mrow / L;
+          const bool nul = p.kn && b >= p.n_cond;
+          const size_t koff = nul ? 0 : (size_t)b * p.kv_sample_stride;
+          const void* kb = nul ? p.kn : p.kc;
+          __syncwarp();
+          for (int idx = lane; idx < p.nk * 16; idx += 32) {
+            const int j = idx >> 4, c4 = (idx & 15) * 4;
+            const size_t g = koff + (size_t)j * p.ldkv + (size_t)h * p.d + c4;
+            float4 kk, vv;
+            if (KIND == 2) {
+              kk = SmemIO<2>::ld4(reinterpret_cast<const __nv_bfloat16*>(kb) + g);
+              vv = SmemIO<2>::ld4(reinterpret_cast<const __nv_bfloat16*>(kb) + g + p.heads * p.d);
+            } else {
+              kk = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(kb) + g);
+              vv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(kb) + g + p.heads * p.d);
+            }
+            *reinterpret_cast<float4*>(Kw + j * A_LD + c4) = kk;
+            *reinterpret_cast<float4*>(Vw + j * A_LD + c4) = vv;
+          }
+          __syncwarp();
+          attend_head_mma<1, KIND>(Qs + (size_t)s * L * A_LD, A_LD, Kw, Vw, A_LD, L, p.nk, p.scale, p.att, ob, p.ldo, lane);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");           // staging is free for the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace tc
+
+static size_t gemm_attn_smem(const GemmAttnParams& p, int nk_max) {
+  const int BN = p.cross ? p.d : 3 * p.d;
+  const size_t stage = tc::A_ABYTES + (((size_t)BN * 128 + 1023) & ~(size_t)1023);
+  size_t stg = (size_t)tc::A_TM * tc::A_LD * 4;   // Qs
+  if (p.cross) stg += (size_t)tc::A_EPI_WARPS * 2 * nk_max * tc::A_LD * 4;
+  else stg += 2 * (size_t)tc::A_TM * tc::A_LD * 4;
+  return tc::A_STAGES * stage + stg + 1024;
+}
+
+bool gemm_attn_supported(int kind, int C, int L, int heads, int d, int cross, int nk_max) {
+  const int kch = kind == 1 ? 32 : 64;
+  if (d != 64 || C % kch || L < 1 || L > 64 || (128 % L) != 0) return false;
+  if (!cross && L > 64) return false;
+  GemmAttnParams p{}; p.cross = cross; p.d = d;
+  return gemm_attn_smem(p, cross ? nk_max : 0) <= 220 * 1024 && (!cross || nk_max <= 64);
+}
+
+cudaError_t init_gemm_attn() {
+  cudaError_t e = cudaFuncSetAttribute(tc::gemm_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(tc::gemm_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+}
+
+static int g_sms_ga = 0;
+
+cudaError_t launch_gemm_attn(const void* tmA, const void* tmB, const GemmAttnParams& p, int kind, cudaStream_t s) {
+  if (p.M <= 0) return cudaSuccess;
+  if (g_sms_ga == 0) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms_ga, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms_ga <= 0) g_sms_ga = 148;
+  }
+  const int BN = p.cross ? p.d : 3 * p.d;
+  const size_t smem = gemm_attn_smem(p, p.nk);
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  const uint32_t fmt = kind == 1 ? 2u : 1u;
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(tc::A_TM >> 4) << 24);
+  const long long tiles = (long long)((p.M + tc::A_TM - 1) / tc::A_TM) * p.heads;
+  const unsigned grid = (unsigned)(tiles < g_sms_ga ? tiles : g_sms_ga);
+  const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(tmA);
+  const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(tmB);
+  if (kind == 1) tc::gemm_attn_kernel<1><<<grid, tc::A_THREADS, smem, s>>>(a, b, p, idesc);
+  else tc::gemm_attn_kernel<2><<<grid, tc::A_THREADS, smem, s>>>(a, b, p, idesc);
+  return cudaGetLastError();
+}
+
+}  // namespace mdt

@@ -173,6 +173,23 @@ bool gemm_tma_shape_ok(int kind, int C, int L, int N);
 cudaError_t init_gemm_tma();
 cudaError_t launch_gemm_tma(const void* tmA, const void* tmB, const TmaGemmParams& p, int kind, cudaStream_t s);
 
+// ---- fused per-head projection + attention (gemm_attn.cu) ------------------------------------------------
+struct GemmAttnParams {
+  int M;                  // valid rows = B_eff * L
+  int heads, d;
+  int kchunks, C;         // K loop over the (LayerNorm-ed) activation channels
+  int L, Sb;              // positions per sample; samples per 128-row tile
+  int cross;              // 0: self-attention (per-head [q|k|v], BN = 3d); 1: cross-attention (q only, BN = d)
+  const float* bias;      // folded bias, repacked per head [heads * BN]
+  float scale;
+  void* att; int ldo;     // head outputs [M][heads * d] in the operand dtype
+  const void* kc; const void* kn;  // cross: conditioning K|V cache [B][nk][2 * heads * d] and the shared null-branch block
+  int ldkv; long long kv_sample_stride; int n_cond; int nk;
+};
+bool gemm_attn_supported(int kind, int C, int L, int heads, int d, int cross, int nk_max);
+cudaError_t init_gemm_attn();
+cudaError_t launch_gemm_attn(const void* tmA, const void* tmB, const GemmAttnParams& p, int kind, cudaStream_t s);
+
 // ---- tensor-core GEMM (gemm_tc.cu) --------------------------------------------------------------
 // kind: 1 = tf32, 2 = bf16.  Wtc must hold the weights pre-converted by convert_weights_tc().
 cudaError_t launch_gemm_tc(const GemmParams& p, int kind, cudaStream_t s);

@@ -55,7 +55,7 @@ struct MdtError {
 // ------------------------------------------------------------------------------------------------
 // program representation
 // ------------------------------------------------------------------------------------------------
-enum OpType { OP_GEMM, OP_GN_STATS, OP_ROW_STATS, OP_ATTN, OP_UPGATHER, OP_PERMUTE, OP_GN_APPLY, OP_LN_APPLY, OP_GEMM_TMA };
+enum OpType { OP_GEMM, OP_GN_STATS, OP_ROW_STATS, OP_ATTN, OP_UPGATHER, OP_PERMUTE, OP_GN_APPLY, OP_LN_APPLY, OP_GEMM_TMA, OP_GEMM_ATTN };
 
 struct Op {
   OpType type = OP_GEMM;
@@ -67,6 +67,7 @@ struct Op {
   GnApplyParams ga{};
   LnApplyParams la{};
   TmaGemmParams tg{};
+  GemmAttnParams gat{};
   alignas(64) unsigned char tmA[128];
   alignas(64) unsigned char tmB[128];
   bool cross = false;  // attention reads the precomputed conditioning K/V
@@ -299,6 +300,22 @@ struct Builder {
     emit(prog, op);
   }
 
+  // fused per-head projection + attention (gemm_attn.cu); dW32 = [heads * BN][C] fp32 on the device, head-major
+  void emit_gemm_attn(std::vector<Op>& prog, const void* A, int C, int L, const float* dW32, const float* bias, int cross,
+                      int cross_layer, const void* kc, const void* kn) {
+    Op op; op.type = OP_GEMM_ATTN; op.rps = L; op.cross = cross != 0; op.cross_layer = cross_layer;
+    const int kch = pl.prec == MDT_PREC_TF32 ? 32 : 64;
+    const int heads = pl.cfg.heads, d = pl.cfg.head_features, BN = cross ? d : 3 * d;
+    GemmAttnParams& g = op.gat;
+    g.M = 0; g.heads = heads; g.d = d; g.kchunks = C / kch; g.C = C; g.L = L; g.Sb = 128 / L; g.cross = cross;
+    g.bias = bias; g.scale = 1.0f / sqrtf((float)d); g.att = pl.att; g.ldo = heads * d;
+    g.kc = kc; g.kn = kn; g.ldkv = 2 * heads * d; g.kv_sample_stride = 0; g.n_cond = 0; g.nk = L;
+    const void* wop = tc_copy(dW32, (size_t)heads * BN * C);
+    if (make_tmap_act(op.tmA, A, pl.prec, C, L, (long long)pl.Beff_max) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(attn activation) failed");
+    if (make_tmap_weight(op.tmB, wop, pl.prec, (long long)C, heads * BN, BN) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(attn weight) failed");
+    emit(prog, op);
+  }
+
   // ResnetBlock1d (modules.py:145-205).  Returns the output buffer (acquired from the pool).
   float* resnet(std::vector<Op>& prog, const std::string& pre, const Src& in, int L, int Cout, int groups,
                 float* forced_out = nullptr) {
@@ -388,6 +405,7 @@ struct Builder {
     const bool fast = tma_ok(C, L, C) && gn_apply_supported(L, C, 32) && tma_ok(C, L, 3 * Hd) && tma_ok(C, L, Hd) &&
                       tma_ok(Hd, L, C) && tma_ok(C, L, mid) && tma_ok(mid, L, C) && C <= 1024;
     const int akind = fast ? pl.prec : 0;
+    const bool fuse_attn = Hd == heads * d && !getenv("MDT_NO_FUSED_ATTN");
     // to_in: GroupNorm(32, eps 1e-6) folded into the 1x1 conv
     std::vector<float> wi(T(pre + "to_in.1.weight", (int64_t)C * C), T(pre + "to_in.1.weight", (int64_t)C * C) + (size_t)C * C);
     std::vector<float> bi(T(pre + "to_in.1.bias", C), T(pre + "to_in.1.bias", C) + C);
@@ -424,7 +442,21 @@ struct Builder {
           std::copy(bq.begin(), bq.end(), b.begin()); std::copy(bkv.begin(), bkv.end(), b.begin() + Hd);
         }
         const float* d_w = upload(w); const float* d_b = upload(b);
-        if (fast) {
+        const bool fuse_self = fast && fuse_attn && gemm_attn_supported(pl.prec, C, L, heads, d, 0, 0);
+        if (fuse_self) {
+          // head-major repack: rows [h][q(64) | k(64) | v(64)]
+          std::vector<float> wr((size_t)3 * Hd * C), br((size_t)3 * Hd);
+          for (int h = 0; h < heads; ++h)
+            for (int part = 0; part < 3; ++part)
+              for (int r = 0; r < d; ++r) {
+                const size_t src = (size_t)part * Hd + (size_t)h * d + r, dst = ((size_t)h * 3 + part) * d + r;
+                memcpy(&wr[dst * C], &w[src * C], (size_t)C * sizeof(float));
+                br[dst] = b[src];
+              }
+          const float* d_wr = upload(wr); const float* d_br = upload(br);
+          emit_ln_apply(prog, t, C, L, tn);
+          emit_gemm_attn(prog, tn, C, L, d_wr, d_br, 0, -1, nullptr, nullptr);
+        } else if (fast) {
           emit_ln_apply(prog, t, C, L, tn);
           emit_gemm_tma(prog, tn, C, L, 1, d_w, d_b, 3 * Hd, 0, nullptr, nullptr, pl.qkv);
         } else {
@@ -441,7 +473,7 @@ struct Builder {
         at.at.kv_sample_stride = (long long)L * 3 * Hd; at.at.k_null = nullptr; at.at.v_null = nullptr; at.at.n_cond = 0;
         at.at.o = pl.att; at.at.ldo = Hd; at.at.nq = L; at.at.nk = L; at.at.heads = heads; at.at.d = d;
         at.at.scale = 1.0f / sqrtf((float)d);
-        emit(prog, at);
+        if (!fuse_self) emit(prog, at);
         const float* d_wo = upload(T(ap + "attention.to_out.weight", (int64_t)C * Hd), (size_t)C * Hd);
         const float* d_bo = upload(T(ap + "attention.to_out.bias", C), C);
         if (fast) {
@@ -471,7 +503,11 @@ struct Builder {
         }
         const int layer = (int)pl.cross.size();
         pl.cross.push_back(cl);
-        if (fast) {
+        const bool fuse_cross = fast && fuse_attn && gemm_attn_supported(pl.prec, C, L, heads, d, 1, pl.cfg.ctx_max_length);
+        if (fuse_cross) {
+          emit_ln_apply(prog, t, C, L, tn);
+          emit_gemm_attn(prog, tn, C, L, d_wq, d_bq, 1, layer, cl.kv_cond_op, cl.kv_null_op);
+        } else if (fast) {
           emit_ln_apply(prog, t, C, L, tn);
           emit_gemm_tma(prog, tn, C, L, 1, d_wq, d_bq, Hd, 0, nullptr, nullptr, pl.qc);
         } else {
@@ -490,7 +526,7 @@ struct Builder {
         }
         at.at.o = pl.att; at.at.ldo = Hd; at.at.nq = L; at.at.heads = heads; at.at.d = d;
         at.at.scale = 1.0f / sqrtf((float)d);
-        emit(prog, at);
+        if (!fuse_cross) emit(prog, at);
         const float* d_wo = upload(T(ap + "attention.to_out.weight", (int64_t)C * Hd), (size_t)C * Hd);
         const float* d_bo = upload(T(ap + "attention.to_out.bias", C), C);
         if (fast) {
@@ -760,6 +796,11 @@ static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_con
       }
       case OP_GN_APPLY: { GnApplyParams g = op.ga; g.B = Beff; CK(launch_gn_apply(g, pl.prec, s)); pl.launches++; break; }
       case OP_LN_APPLY: { LnApplyParams l = op.la; l.rows = (long long)Beff * op.rps; CK(launch_ln_apply(l, pl.prec, s)); pl.launches++; break; }
+      case OP_GEMM_ATTN: {
+        GemmAttnParams g = op.gat; g.M = Beff * op.rps;
+        if (op.cross) { g.nk = n_ctx; g.kv_sample_stride = (long long)n_ctx * g.ldkv; g.n_cond = n_cond; }
+        CK(launch_gemm_attn(op.tmA, op.tmB, g, pl.prec, s)); pl.launches++; break;
+      }
       case OP_GEMM_TMA: { TmaGemmParams g = op.tg; g.M = Beff * op.rps; CK(launch_gemm_tma(op.tmA, op.tmB, g, pl.prec, s)); pl.launches++; break; }
       case OP_UPGATHER: CK(launch_upsample_gather(op.in0, op.in1, op.in2, op.out, Beff, op.i0, op.i1, op.i2, s)); pl.launches++; break;
       case OP_PERMUTE: CK(launch_patch_permute(op.in0, op.out, Beff, op.i0, op.i1, op.i2, op.i3, s)); pl.launches++; break;
@@ -910,6 +951,7 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
     CK(init_kernels());
     CK(init_gemm_tc());
     CK(init_gemm_tma());
+    CK(init_gemm_attn());
     pl->cfg = *cfg; pl->device = device; pl->prec = cfg->precision;
     pl->P = cfg->in_channels; pl->L0 = cfg->length; pl->Hd = cfg->heads * cfg->head_features; pl->F = cfg->ctx_features;
     pl->Bmax = cfg->max_batch; pl->Beff_max = 2 * cfg->max_batch;
