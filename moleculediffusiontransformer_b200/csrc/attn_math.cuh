@@ -14,12 +14,14 @@ template <> struct SmemIO<0> {
   static __device__ __forceinline__ float4 ld4(const T* p) { return *reinterpret_cast<const float4*>(p); }
   static __device__ __forceinline__ float ld1(const T* p) { return *p; }
   static __device__ __forceinline__ void st(void* o, size_t i, float v) { reinterpret_cast<float*>(o)[i] = v; }
+  static __device__ __forceinline__ void st2(void* o, size_t i, float a, float b) { *reinterpret_cast<float2*>(reinterpret_cast<float*>(o) + i) = make_float2(a, b); }
 };
 template <> struct SmemIO<1> {
   typedef float T;
   static __device__ __forceinline__ float4 ld4(const T* p) { return *reinterpret_cast<const float4*>(p); }
   static __device__ __forceinline__ float ld1(const T* p) { return *p; }
   static __device__ __forceinline__ void st(void* o, size_t i, float v) { reinterpret_cast<uint32_t*>(o)[i] = tc::to_tf32(v); }
+  static __device__ __forceinline__ void st2(void* o, size_t i, float a, float b) { *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(o) + i) = make_uint2(tc::to_tf32(a), tc::to_tf32(b)); }
 };
 template <> struct SmemIO<2> {
   typedef __nv_bfloat16 T;
@@ -31,6 +33,7 @@ template <> struct SmemIO<2> {
   }
   static __device__ __forceinline__ float ld1(const T* p) { return __bfloat162float(*p); }
   static __device__ __forceinline__ void st(void* o, size_t i, float v) { reinterpret_cast<__nv_bfloat16*>(o)[i] = __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ void st2(void* o, size_t i, float a, float b) { *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(o) + i) = tc::pack_bf16(a, b); }
 };
 
 // One (sample, head): q rows at qs (stride sa), k rows at ks and v rows at vs (stride sb); ss = nq x (nk + 1) scratch.
@@ -125,20 +128,22 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int SK, int OK>
-__device__ __forceinline__ void attend_head_mma(const typename SmemIO<SK>::T* qs, int sa, const typename SmemIO<SK>::T* ks,
-                                                const typename SmemIO<SK>::T* vs, int sb, int nq, int nk, float scale, void* out,
-                                                size_t out_base, int ldo, int lane) {
+// NT = number of 8-key tiles held in registers (compile time, so no predicated-off MMA slots are issued).
+template <int SK, int OK, int NT>
+__device__ __forceinline__ void attend_head_mma_nt(const typename SmemIO<SK>::T* qs, int sa, const typename SmemIO<SK>::T* ks,
+                                                   const typename SmemIO<SK>::T* vs, int sb, int nq, int nk, float scale, void* out,
+                                                   size_t out_base, int ldo, int lane) {
   typedef SmemIO<SK> IO;
   typedef SmemIO<OK> OUT;
-  constexpr int MAXNT = 8;                       // nk <= 64
-  const int nt = (nk + 7) >> 3;
   const int g = lane >> 2, q = lane & 3;
   for (int i0 = 0; i0 < nq; i0 += 16) {
     const int r0 = min(i0 + g, nq - 1), r1 = min(i0 + g + 8, nq - 1);
-    float sc[MAXNT][4];
+    float sc[NT][4];
 #pragma unroll
-    for (int t = 0; t < MAXNT; ++t) { sc[t][0] = 0.f; sc[t][1] = 0.f; sc[t][2] = 0.f; sc[t][3] = 0.f; }
+    for (int t = 0; t < NT; ++t) { sc[t][0] = 0.f; sc[t][1] = 0.f; sc[t][2] = 0.f; sc[t][3] = 0.f; }
+    int jr[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) jr[t] = min(t * 8 + g, nk - 1) * sb;
 #pragma unroll
     for (int k0 = 0; k0 < 64; k0 += 8) {
       uint32_t a[4];
@@ -147,39 +152,32 @@ __device__ __forceinline__ void attend_head_mma(const typename SmemIO<SK>::T* qs
       a[2] = __float_as_uint(IO::ld1(qs + r0 * sa + k0 + q + 4));
       a[3] = __float_as_uint(IO::ld1(qs + r1 * sa + k0 + q + 4));
 #pragma unroll
-      for (int t = 0; t < MAXNT; ++t) {
-        if (t < nt) {
-          const int j = min(t * 8 + g, nk - 1);
-          const uint32_t b0 = __float_as_uint(IO::ld1(ks + j * sb + k0 + q));
-          const uint32_t b1 = __float_as_uint(IO::ld1(ks + j * sb + k0 + q + 4));
-          mma_tf32_16x8x8(sc[t], a, b0, b1);
-        }
+      for (int t = 0; t < NT; ++t) {
+        const uint32_t b0 = __float_as_uint(IO::ld1(ks + jr[t] + k0 + q));
+        const uint32_t b1 = __float_as_uint(IO::ld1(ks + jr[t] + k0 + q + 4));
+        mma_tf32_16x8x8(sc[t], a, b0, b1);
       }
     }
     // softmax over keys: thread holds columns 8t + 2q, 8t + 2q + 1 of rows g (c0, c1) and g + 8 (c2, c3)
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-    for (int t = 0; t < MAXNT; ++t) {
-      if (t < nt) {
-        const int j = t * 8 + 2 * q;
-        sc[t][0] = (j < nk) ? sc[t][0] * scale : -INFINITY;
-        sc[t][1] = (j + 1 < nk) ? sc[t][1] * scale : -INFINITY;
-        sc[t][2] = (j < nk) ? sc[t][2] * scale : -INFINITY;
-        sc[t][3] = (j + 1 < nk) ? sc[t][3] * scale : -INFINITY;
-        m0 = fmaxf(m0, fmaxf(sc[t][0], sc[t][1]));
-        m1 = fmaxf(m1, fmaxf(sc[t][2], sc[t][3]));
-      }
+    for (int t = 0; t < NT; ++t) {
+      const int j = t * 8 + 2 * q;
+      sc[t][0] = (j < nk) ? sc[t][0] * scale : -INFINITY;
+      sc[t][1] = (j + 1 < nk) ? sc[t][1] * scale : -INFINITY;
+      sc[t][2] = (j < nk) ? sc[t][2] * scale : -INFINITY;
+      sc[t][3] = (j + 1 < nk) ? sc[t][3] * scale : -INFINITY;
+      m0 = fmaxf(m0, fmaxf(sc[t][0], sc[t][1]));
+      m1 = fmaxf(m1, fmaxf(sc[t][2], sc[t][3]));
     }
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int t = 0; t < MAXNT; ++t) {
-      if (t < nt) {
-        sc[t][0] = expf(sc[t][0] - m0); sc[t][1] = expf(sc[t][1] - m0);
-        sc[t][2] = expf(sc[t][2] - m1); sc[t][3] = expf(sc[t][3] - m1);
-        s0 += sc[t][0] + sc[t][1]; s1 += sc[t][2] + sc[t][3];
-      }
+    for (int t = 0; t < NT; ++t) {
+      sc[t][0] = expf(sc[t][0] - m0); sc[t][1] = expf(sc[t][1] - m0);
+      sc[t][2] = expf(sc[t][2] - m1); sc[t][3] = expf(sc[t][3] - m1);
+      s0 += sc[t][0] + sc[t][1]; s1 += sc[t][2] + sc[t][3];
     }
     s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
     s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
@@ -189,35 +187,38 @@ __device__ __forceinline__ void attend_head_mma(const typename SmemIO<SK>::T* qs
 #pragma unroll
     for (int n = 0; n < 8; ++n) { oc[n][0] = 0.f; oc[n][1] = 0.f; oc[n][2] = 0.f; oc[n][3] = 0.f; }
 #pragma unroll
-    for (int t = 0; t < MAXNT; ++t) {
-      if (t < nt) {
-        uint32_t a[4];
-        a[0] = tc::to_tf32(sc[t][0] * inv0);   // (row g,     key 8t + 2q)
-        a[1] = tc::to_tf32(sc[t][2] * inv1);   // (row g + 8, key 8t + 2q)
-        a[2] = tc::to_tf32(sc[t][1] * inv0);   // (row g,     key 8t + 2q + 1)
-        a[3] = tc::to_tf32(sc[t][3] * inv1);   // (row g + 8, key 8t + 2q + 1)
-        const int j0 = min(t * 8 + 2 * q, nk - 1), j1 = min(t * 8 + 2 * q + 1, nk - 1);   // masked keys carry p = 0
+    for (int t = 0; t < NT; ++t) {
+      uint32_t a[4];
+      a[0] = tc::to_tf32(sc[t][0] * inv0);   // (row g,     key 8t + 2q)
+      a[1] = tc::to_tf32(sc[t][2] * inv1);   // (row g + 8, key 8t + 2q)
+      a[2] = tc::to_tf32(sc[t][1] * inv0);   // (row g,     key 8t + 2q + 1)
+      a[3] = tc::to_tf32(sc[t][3] * inv1);   // (row g + 8, key 8t + 2q + 1)
+      const int j0 = min(t * 8 + 2 * q, nk - 1) * sb, j1 = min(t * 8 + 2 * q + 1, nk - 1) * sb;   // masked keys carry p = 0
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-          const uint32_t b0 = __float_as_uint(IO::ld1(vs + j0 * sb + n * 8 + g));
-          const uint32_t b1 = __float_as_uint(IO::ld1(vs + j1 * sb + n * 8 + g));
-          mma_tf32_16x8x8(oc[n], a, b0, b1);
-        }
+      for (int n = 0; n < 8; ++n) {
+        const uint32_t b0 = __float_as_uint(IO::ld1(vs + j0 + n * 8 + g));
+        const uint32_t b1 = __float_as_uint(IO::ld1(vs + j1 + n * 8 + g));
+        mma_tf32_16x8x8(oc[n], a, b0, b1);
       }
     }
+    const bool ok0 = i0 + g < nq, ok1 = i0 + g + 8 < nq;
+    const size_t o0 = out_base + (size_t)(i0 + g) * ldo + 2 * q, o1 = o0 + (size_t)8 * ldo;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      const int col = n * 8 + 2 * q;
-      if (i0 + g < nq) {
-        const size_t o = out_base + (size_t)(i0 + g) * ldo + col;
-        OUT::st(out, o, oc[n][0]); OUT::st(out, o + 1, oc[n][1]);
-      }
-      if (i0 + g + 8 < nq) {
-        const size_t o = out_base + (size_t)(i0 + g + 8) * ldo + col;
-        OUT::st(out, o, oc[n][2]); OUT::st(out, o + 1, oc[n][3]);
-      }
+      if (ok0) OUT::st2(out, o0 + n * 8, oc[n][0], oc[n][1]);
+      if (ok1) OUT::st2(out, o1 + n * 8, oc[n][2], oc[n][3]);
     }
   }
+}
+
+template <int SK, int OK>
+__device__ __forceinline__ void attend_head_mma(const typename SmemIO<SK>::T* qs, int sa, const typename SmemIO<SK>::T* ks,
+                                                const typename SmemIO<SK>::T* vs, int sb, int nq, int nk, float scale, void* out,
+                                                size_t out_base, int ldo, int lane) {
+  if (nk <= 8) attend_head_mma_nt<SK, OK, 1>(qs, sa, ks, vs, sb, nq, nk, scale, out, out_base, ldo, lane);
+  else if (nk <= 16) attend_head_mma_nt<SK, OK, 2>(qs, sa, ks, vs, sb, nq, nk, scale, out, out_base, ldo, lane);
+  else if (nk <= 32) attend_head_mma_nt<SK, OK, 4>(qs, sa, ks, vs, sb, nq, nk, scale, out, out_base, ldo, lane);
+  else attend_head_mma_nt<SK, OK, 8>(qs, sa, ks, vs, sb, nq, nk, scale, out, out_base, ldo, lane);
 }
 
 }  // namespace mdt
