@@ -127,13 +127,23 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
         const int col0 = half * cols_per_warp + cc;
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0), v);
         float* dst = (col0 < 64 ? Qs : (col0 < 128 ? Ks : Vs)) + (size_t)row * A_LD + (col0 & 63);
-        const float* bias = p.bias + h * BN + col0;
+        if (col0 < 64) {
+          // only q carries a bias here: the k bias shifts every score of a query equally (cancels in the softmax) and
+          // the v bias passes through the row-stochastic attention matrix unchanged (folded into the out-projection bias)
+          const float* bias = p.bias + h * p.d + col0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + j * 4));
-          *reinterpret_cast<uint4*>(dst + j * 4) =
-              make_uint4(to_tf32(__uint_as_float(v[4 * j]) + bv.x), to_tf32(__uint_as_float(v[4 * j + 1]) + bv.y),
-                         to_tf32(__uint_as_float(v[4 * j + 2]) + bv.z), to_tf32(__uint_as_float(v[4 * j + 3]) + bv.w));
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + j * 4));
+            *reinterpret_cast<uint4*>(dst + j * 4) =
+                make_uint4(to_tf32(__uint_as_float(v[4 * j]) + bv.x), to_tf32(__uint_as_float(v[4 * j + 1]) + bv.y),
+                           to_tf32(__uint_as_float(v[4 * j + 2]) + bv.z), to_tf32(__uint_as_float(v[4 * j + 3]) + bv.w));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(dst + j * 4) =
+                make_uint4(to_tf32(__uint_as_float(v[4 * j])), to_tf32(__uint_as_float(v[4 * j + 1])),
+                           to_tf32(__uint_as_float(v[4 * j + 2])), to_tf32(__uint_as_float(v[4 * j + 3])));
         }
       }
       tc_fence_before();

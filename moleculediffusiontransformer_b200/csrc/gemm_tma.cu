@@ -9,7 +9,7 @@
 //   warp 1     one lane issues tcgen05.mma (accumulator in TMEM), tcgen05.commit frees stages; owns TMEM
 //   warps 2-5  epilogue: tcgen05.ld -> smem staging -> coalesced bias / GELU / residual, fp32 and/or
 //              operand-dtype stores
-// Persistent, one CTA per SM: 5-stage smem ring, two TMEM accumulators so the epilogue of tile i overlaps tile i+1.
+// Persistent, one CTA per SM: 4-stage smem ring, 16 epilogue warps, two TMEM accumulators so the epilogue of tile i overlaps tile i+1.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "aload.cuh"
@@ -19,11 +19,11 @@ namespace mdt {
 namespace tc {
 
 constexpr int T_TM = 128;
-constexpr int T_STAGES = 5;
+constexpr int T_STAGES = 4;
 constexpr int T_A_BYTES = T_TM * 128;
 constexpr int T_B_BYTES = 128 * 128;
 constexpr int T_STAGE_BYTES = T_A_BYTES + T_B_BYTES;
-constexpr int T_EPI_WARPS = 8;
+constexpr int T_EPI_WARPS = 16;
 constexpr int T_STG_LD = 36;                                  // 32 columns + 4 floats of padding per staged row
 constexpr int T_STG_BYTES = T_EPI_WARPS * 32 * T_STG_LD * 4;  // per-warp private staging, 4.5 KB each
 constexpr int T_SMEM_BYTES = T_STAGES * T_STAGE_BYTES + T_STG_BYTES + 1024;
@@ -119,12 +119,14 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
-    const int ew = warp - 2;             // 0..7
+    const int ew = warp - 2;             // 0..15
     const int q = warp & 3;              // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;            // column half handled by this warp
+    const int half = ew >> 2;            // column group (0..3) handled by this warp
     float* stg = reinterpret_cast<float*>(smem + T_STAGES * T_STAGE_BYTES) + (size_t)ew * 32 * T_STG_LD;
-    const int cols_per_half = BN >= 64 ? BN / 2 : BN;   // narrow tiles: only the first four warps work
-    const bool active = BN >= 64 || half == 0;
+    // BN = 128: four groups of 32 columns; BN = 64: two groups; narrower tiles: one group
+    const int ngroups = BN >= 128 ? 4 : (BN >= 64 ? 2 : 1);
+    const int cols_per_half = BN / ngroups;
+    const bool active = half < ngroups;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int mt = t / n_tiles, nt = t - mt * n_tiles;

@@ -180,7 +180,7 @@ struct GemmAttnParams {
   int kchunks, C;         // K loop over the (LayerNorm-ed) activation channels
   int L, Sb;              // positions per sample; samples per 128-row tile
   int cross;              // 0: self-attention (per-head [q|k|v], BN = 3d); 1: cross-attention (q only, BN = d)
-  const float* bias;      // folded bias, repacked per head [heads * BN]
+  const float* bias;      // folded q bias [heads * d] (k bias cancels in the softmax; v bias is folded into the out-projection)
   float scale;
   void* att; int ldo;     // head outputs [M][heads * d] in the operand dtype
   const void* kc; const void* kn;  // cross: conditioning K|V cache [B][nk][2 * heads * d] and the shared null-branch block

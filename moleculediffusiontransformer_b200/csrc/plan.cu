@@ -318,7 +318,8 @@ struct Builder {
 
   // ResnetBlock1d (modules.py:145-205).  Returns the output buffer (acquired from the pool).
   float* resnet(std::vector<Op>& prog, const std::string& pre, const Src& in, int L, int Cout, int groups,
-                float* forced_out = nullptr) {
+                float* forced_out = nullptr, void** out_op = nullptr) {
+    if (out_op) *out_op = nullptr;
     const int Cin = in.C();
     const int M = pl.cfg.mapping_features;
     // block1: GN(groups) -> SiLU -> conv3
@@ -380,7 +381,9 @@ struct Builder {
     if (ok2) {
       float* a2 = a1 ? a1 : acquire();   // a1 is dead once conv1 has run
       emit_gn_apply(prog, hs, L, groups, 1e-5f, f.aff, 2 * Cout, pl.d_call, 1, a2, nullptr);
-      emit_gemm_tma(prog, a2, Cout, L, 3, d_w2, d_b2, Cout, 0, res, out, nullptr);
+      void* oc = nullptr;
+      if (out_op) { oc = acquire(); *out_op = oc; }
+      emit_gemm_tma(prog, a2, Cout, L, 3, d_w2, d_b2, Cout, 0, res, out, oc);
       if (!a1) release(a2);
     } else {
       gn_stats(prog, hs, L, groups, 1e-5f);
@@ -453,9 +456,10 @@ struct Builder {
                 memcpy(&wr[dst * C], &w[src * C], (size_t)C * sizeof(float));
                 br[dst] = b[src];
               }
-          const float* d_wr = upload(wr); const float* d_br = upload(br);
+          const float* d_wr = upload(wr);
+          const float* d_bq = upload(b.data(), Hd);      // q bias only (see gemm_attn.cu)
           emit_ln_apply(prog, t, C, L, tn);
-          emit_gemm_attn(prog, tn, C, L, d_wr, d_br, 0, -1, nullptr, nullptr);
+          emit_gemm_attn(prog, tn, C, L, d_wr, d_bq, 0, -1, nullptr, nullptr);
         } else if (fast) {
           emit_ln_apply(prog, t, C, L, tn);
           emit_gemm_tma(prog, tn, C, L, 1, d_w, d_b, 3 * Hd, 0, nullptr, nullptr, pl.qkv);
@@ -475,7 +479,17 @@ struct Builder {
         at.at.scale = 1.0f / sqrtf((float)d);
         if (!fuse_self) emit(prog, at);
         const float* d_wo = upload(T(ap + "attention.to_out.weight", (int64_t)C * Hd), (size_t)C * Hd);
-        const float* d_bo = upload(T(ap + "attention.to_out.bias", C), C);
+        std::vector<float> bo(T(ap + "attention.to_out.bias", C), T(ap + "attention.to_out.bias", C) + C);
+        if (fuse_self) {
+          // v bias passes through softmax-weighted averaging unchanged: out += Wo b_v
+          const float* wo = T(ap + "attention.to_out.weight", (int64_t)C * Hd);
+          for (int n = 0; n < C; ++n) {
+            double acc = 0.0;
+            for (int k = 0; k < Hd; ++k) acc += (double)wo[(size_t)n * Hd + k] * (double)b[(size_t)2 * Hd + k];
+            bo[n] = (float)((double)bo[n] + acc);
+          }
+        }
+        const float* d_bo = upload(bo);
         if (fast) {
           // without a cross-attention stage the raw operand copy of the new token stream feeds FF1 directly
           emit_gemm_tma(prog, pl.att, Hd, L, 1, d_wo, d_bo, C, 0, t, t, has_cross ? nullptr : (void*)tn);
@@ -642,7 +656,8 @@ struct Builder {
     // ---- UNet program (UNet1d.forward, modules.py:1144-1180)
     const std::string U = "unet.";
     Src xin{pl.xin, c.in_channels, nullptr, 0, 1.f};
-    float* cur = resnet(prog, U + "to_in.block.", xin, c.length, Cin0, 1);
+    void* cur_op = nullptr;   // operand-dtype copy of the current activation (feeds the TMA down-sampling conv)
+    float* cur = resnet(prog, U + "to_in.block.", xin, c.length, Cin0, 1, nullptr, p == 1 ? &cur_op : nullptr);
     if (p > 1) {
       float* pt = acquire();
       Op op; op.type = OP_PERMUTE; op.in0 = cur; op.out = pt; op.i0 = Ll[0]; op.i1 = Cin0; op.i2 = p; op.i3 = 1;
@@ -658,12 +673,27 @@ struct Builder {
       const std::string dp = U + "downsamples." + std::to_string(i) + ".";
       const int f = c.factors[i], k = f * c.kernel_multiplier_downsample + 1, pad = f * (c.kernel_multiplier_downsample / 2);
       const int Ci = Cl[i], Co = Cl[i + 1], Lo = Ll[i + 1];
-      auto wd = pack_conv(T(dp + "downsample.weight", (int64_t)Co * Ci * k), Co, Ci, k);
-      const float* d_wd = upload(wd);
+      const float* wraw = T(dp + "downsample.weight", (int64_t)Co * Ci * k);
       const float* d_bd = upload(T(dp + "downsample.bias", Co), Co);
       float* y = acquire();
-      Src xs{xcur, Ci, nullptr, 0, 1.f};
-      emit(prog, gemm_op(make_aload(xs, Ll[i], Lo, k, f, pad), d_wd, tc_copy(d_wd, wd.size()), d_bd, Co, 0, nullptr, y, Lo));
+      if (cur_op && k == 2 * f + 1 && pad == f && tma_ok(f * Ci, Lo, Co)) {
+        // strided conv as a 3-tap stride-1 conv over f packed positions: [B][L][C] viewed as [B][L/f][f*C];
+        // input f*o - f + kk = packed position o - 1 + kk / f, sub-position kk % f (the last tap uses sub-position 0 only)
+        const int Cp = f * Ci;
+        std::vector<float> wp((size_t)Co * 3 * Cp, 0.f);
+        for (int co = 0; co < Co; ++co)
+          for (int ci = 0; ci < Ci; ++ci)
+            for (int kk = 0; kk < k; ++kk)
+              wp[((size_t)co * 3 + kk / f) * Cp + (size_t)(kk % f) * Ci + ci] = wraw[((size_t)co * Ci + ci) * k + kk];
+        const float* d_wp = upload(wp);
+        emit_gemm_tma(prog, cur_op, Cp, Lo, 3, d_wp, d_bd, Co, 0, nullptr, y, nullptr);
+      } else {
+        auto wd = pack_conv(wraw, Co, Ci, k);
+        const float* d_wd = upload(wd);
+        Src xs{xcur, Ci, nullptr, 0, 1.f};
+        emit(prog, gemm_op(make_aload(xs, Ll[i], Lo, k, f, pad), d_wd, tc_copy(d_wd, wd.size()), d_bd, Co, 0, nullptr, y, Lo));
+      }
+      if (cur_op) { release(reinterpret_cast<float*>(cur_op)); cur_op = nullptr; }
       set_tap(prog, "down" + std::to_string(i) + ".downsample", y, Lo, Co);
       if (xcur_owned) release(xcur);
       xcur = y; xcur_owned = true;
@@ -681,8 +711,9 @@ struct Builder {
         skips[i].push_back(r);
         xcur = r;
       }
+      const bool more_levels = (i + 1 < nlev);
       if (c.attentions[i] > 0) {
-        float* t = transformer(prog, dp + "transformer.", xcur, Lo, Co, true);
+        float* t = transformer(prog, dp + "transformer.", xcur, Lo, Co, true, more_levels ? &cur_op : nullptr);
         set_tap(prog, "down" + std::to_string(i) + ".tr", t, Lo, Co);
         skips[i].push_back(t);
         xcur = t;
