@@ -175,8 +175,9 @@ __device__ __forceinline__ void attend_head_mma_nt(const typename SmemIO<SK>::T*
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-      sc[t][0] = expf(sc[t][0] - m0); sc[t][1] = expf(sc[t][1] - m0);
-      sc[t][2] = expf(sc[t][2] - m1); sc[t][3] = expf(sc[t][3] - m1);
+      // tensor-core modes only (operands are already tf32 / bf16): ex2.approx is ~2 ulp, far below operand rounding
+      sc[t][0] = __expf(sc[t][0] - m0); sc[t][1] = __expf(sc[t][1] - m0);
+      sc[t][2] = __expf(sc[t][2] - m1); sc[t][3] = __expf(sc[t][3] - m1);
       s0 += sc[t][0] + sc[t][1]; s1 += sc[t][2] + sc[t][3];
     }
     s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);

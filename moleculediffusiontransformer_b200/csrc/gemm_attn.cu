@@ -114,6 +114,11 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
     // cross: warp-private K / V scratch [nk][A_LD] each, carved from the Ks region onwards
     float* Kw = Ks + (size_t)ew * 2 * p.nk * A_LD;
     float* Vw = Kw + (size_t)p.nk * A_LD;
+    // sample ownership: with L <= 32 a quadrant (32 rows) holds 32 / L whole samples, shared by its two warps
+    const bool quad_local = L <= 32;
+    const int spq = quad_local ? 32 / L : 0;                       // samples per quadrant
+    const int s_begin = quad_local ? q * spq : 0, s_end = quad_local ? (q + 1) * spq : p.Sb;
+    const int s_lane = quad_local ? half : ew, s_step = quad_local ? 2 : A_EPI_WARPS;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int mt = t / p.heads, h = t - mt * p.heads;
@@ -147,9 +152,12 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
         }
       }
       tc_fence_before();
-      asm volatile("bar.sync 1, 256;" ::: "memory");           // q / k / v of the whole tile are staged
+      // rows 32q .. 32q + 31 (whole samples when L <= 32) are staged by the two warps of quadrant q only, so a
+      // 64-thread named barrier per quadrant is enough; quadrants drift apart and overlap staging with attention
+      if (quad_local) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      else asm volatile("bar.sync 1, 256;" ::: "memory");
       if (lane == 0) mbar_arrive(&acc_empty[buf]);             // the accumulator may be overwritten now
-      for (int s = ew; s < p.Sb; s += A_EPI_WARPS) {
+      for (int s = s_begin + s_lane; s < s_end; s += s_step) {
         const int mrow = m0 + s * L;
         if (mrow >= p.M) break;
         const size_t ob = (size_t)mrow * p.ldo + (size_t)h * p.d;
@@ -180,7 +188,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
           attend_head_mma<1, KIND>(Qs + (size_t)s * L * A_LD, A_LD, Kw, Vw, A_LD, L, p.nk, p.scale, p.att, ob, p.ldo, lane);
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");           // staging is free for the next tile
+      if (quad_local) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // staging is free for the next tile
+      else asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   }
   tc_fence_before();
