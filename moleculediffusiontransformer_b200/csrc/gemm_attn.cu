@@ -112,13 +112,32 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
     const int cols_per_warp = BN / 2;       // 96 (self) or 32 (cross)
     const int L = p.L;
     // cross: warp-private K / V scratch [nk][A_LD] each, carved from the Ks region onwards
-    float* Kw = Ks + (size_t)ew * 2 * p.nk * A_LD;
+    float* Kw = Ks + (size_t)ew * 4 * p.nk * A_LD;   // two [K | V] buffers per warp (prefetch one sample ahead)
     float* Vw = Kw + (size_t)p.nk * A_LD;
+    const int kvbuf = 2 * p.nk * A_LD;
     // sample ownership: with L <= 32 a quadrant (32 rows) holds 32 / L whole samples, shared by its two warps
     const bool quad_local = L <= 32;
     const int spq = quad_local ? 32 / L : 0;                       // samples per quadrant
     const int s_begin = quad_local ? q * spq : 0, s_end = quad_local ? (q + 1) * spq : p.Sb;
     const int s_lane = quad_local ? half : ew, s_step = quad_local ? 2 : A_EPI_WARPS;
+    int pf_buf = 0;
+    bool pf_primed = false;
+    // cp.async copy of the K / V rows of (tile tt, sample ss) for this tile's head into scratch buffer `bufi`
+    auto issue_kv = [&](int tt, int ss, int bufi) {
+      const int mtt = tt / p.heads, hh = tt - mtt * p.heads;
+      const int b = (mtt * A_TM + ss * L) / L;
+      const bool nul = p.kn && b >= p.n_cond;
+      const float* kb = reinterpret_cast<const float*>(nul ? p.kn : p.kc) + (nul ? 0 : (size_t)b * p.kv_sample_stride) + (size_t)hh * p.d;
+      float* kd = Kw + bufi * kvbuf;
+      float* vd = Vw + bufi * kvbuf;
+      for (int idx = lane; idx < p.nk * 16; idx += 32) {
+        const int j = idx >> 4, c4 = (idx & 15) * 4;
+        const float* src = kb + (size_t)j * p.ldkv + c4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(kd + j * A_LD + c4)), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(vd + j * A_LD + c4)), "l"(src + p.heads * p.d) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int mt = t / p.heads, h = t - mt * p.heads;
@@ -164,6 +183,20 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
         if (!p.cross) {
           attend_head_mma<1, KIND>(Qs + (size_t)s * L * A_LD, A_LD, Ks + (size_t)s * L * A_LD, Vs + (size_t)s * L * A_LD, A_LD, L, L,
                                    p.scale, p.att, ob, p.ldo, lane);
+        } else if (KIND == 1) {
+          // fp32-storage K/V cache: the copy for this item was issued one item ago with cp.async; issue the next one now
+          if (!pf_primed) { issue_kv(t, s, pf_buf); pf_primed = true; }
+          int nt = t, ns = s + s_step;
+          if (ns >= s_end || nt / p.heads * A_TM + ns * L >= p.M) { nt = t + gridDim.x; ns = s_begin + s_lane; }
+          const bool has_next = nt < total_tiles && ns < s_end && (nt / p.heads) * A_TM + ns * L < p.M;
+          if (has_next) issue_kv(nt, ns, pf_buf ^ 1);
+          if (has_next) asm volatile("cp.async.wait_group 1;" ::: "memory");
+          else asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncwarp();
+          attend_head_mma<1, KIND>(Qs + (size_t)s * L * A_LD, A_LD, Kw + pf_buf * kvbuf, Vw + pf_buf * kvbuf, A_LD, L, p.nk, p.scale,
+                                   p.att, ob, p.ldo, lane);
+          __syncwarp();
+          pf_buf ^= 1;
         } else {
           const int b = mrow / L;
           const bool nul = p.kn && b >= p.n_cond;
@@ -173,14 +206,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
           for (int idx = lane; idx < p.nk * 16; idx += 32) {
             const int j = idx >> 4, c4 = (idx & 15) * 4;
             const size_t g = koff + (size_t)j * p.ldkv + (size_t)h * p.d + c4;
-            float4 kk, vv;
-            if (KIND == 2) {
-              kk = SmemIO<2>::ld4(reinterpret_cast<const __nv_bfloat16*>(kb) + g);
-              vv = SmemIO<2>::ld4(reinterpret_cast<const __nv_bfloat16*>(kb) + g + p.heads * p.d);
-            } else {
-              kk = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(kb) + g);
-              vv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(kb) + g + p.heads * p.d);
-            }
+            const float4 kk = SmemIO<2>::ld4(reinterpret_cast<const __nv_bfloat16*>(kb) + g);
+            const float4 vv = SmemIO<2>::ld4(reinterpret_cast<const __nv_bfloat16*>(kb) + g + p.heads * p.d);
             *reinterpret_cast<float4*>(Kw + j * A_LD + c4) = kk;
             *reinterpret_cast<float4*>(Vw + j * A_LD + c4) = vv;
           }
@@ -203,7 +230,7 @@ static size_t gemm_attn_smem(const GemmAttnParams& p, int nk_max) {
   const int BN = p.cross ? p.d : 3 * p.d;
   const size_t stage = tc::A_ABYTES + (((size_t)BN * 128 + 1023) & ~(size_t)1023);
   size_t stg = (size_t)tc::A_TM * tc::A_LD * 4;   // Qs
-  if (p.cross) stg += (size_t)tc::A_EPI_WARPS * 2 * nk_max * tc::A_LD * 4;
+  if (p.cross) stg += (size_t)tc::A_EPI_WARPS * 2 * 2 * nk_max * tc::A_LD * 4;   // per warp: two [K | V] scratch buffers
   else stg += 2 * (size_t)tc::A_TM * tc::A_LD * 4;
   return tc::A_STAGES * stage + stg + 1024;
 }

@@ -116,6 +116,74 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p, co
   }
 }
 
+// Register-resident variant for groups of <= 1024 elements (every ResnetBlock / Transformer1d GroupNorm below level 0):
+// a segment of SEG lanes (power of two) owns one (sample, group); each lane keeps its float4 pieces in registers across the
+// two statistics passes and the apply pass, so the tensor is read exactly once and no shared memory or block barrier is used.
+template <int KIND, int MAXP>
+__global__ void __launch_bounds__(256) gn_apply_reg_kernel(const GnApplyParams p, const int seg, const int pieces) {
+  const int C = p.c0 + p.c1, L = p.L, cpg = C / p.groups, q4 = cpg >> 2;   // q4 = float4 per row segment
+  const int lane = threadIdx.x & 31;
+  const int gpw = 32 / seg;                                               // (sample, group) items per warp
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long item = warp_global * gpw + lane / seg;
+  const int sl = lane % seg;
+  const long long items = (long long)p.B * p.groups;
+  const bool on = item < items;
+  const int b = on ? (int)(item / p.groups) : 0, g = on ? (int)(item % p.groups) : 0;
+  float4 v[MAXP];
+  int rowc[MAXP];   // packed (l << 16) | channel
+  float sum = 0.f;
+#pragma unroll
+  for (int u = 0; u < MAXP; ++u) {
+    const int i = sl + u * seg;
+    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    rowc[u] = -1;
+    if (on && i < pieces) {
+      const int l = i / q4, c = g * cpg + (i - l * q4) * 4;
+      rowc[u] = (l << 16) | c;
+      const size_t row = (size_t)b * L + l;
+      if (c < p.c0) v[u] = __ldg(reinterpret_cast<const float4*>(p.src0 + row * p.c0 + c));
+      else {
+        v[u] = __ldg(reinterpret_cast<const float4*>(p.src1 + row * p.c1 + (c - p.c0)));
+        v[u].x *= p.scale1; v[u].y *= p.scale1; v[u].z *= p.scale1; v[u].w *= p.scale1;
+      }
+      sum += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+    }
+  }
+  for (int o = seg >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float n = (float)(cpg * L);
+  const float mean = sum / n;
+  float sq = 0.f;
+#pragma unroll
+  for (int u = 0; u < MAXP; ++u) {
+    if (rowc[u] >= 0) {
+      const float a = v[u].x - mean, bb = v[u].y - mean, cc = v[u].z - mean, d = v[u].w - mean;
+      sq = fmaf(a, a, sq); sq = fmaf(bb, bb, sq); sq = fmaf(cc, cc, sq); sq = fmaf(d, d, sq);
+    }
+  }
+  for (int o = seg >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = 1.0f / sqrtf(sq / n + p.eps);
+  const float* aff = nullptr;
+  if (p.aff) aff = p.aff + (size_t)(p.call_idx ? *p.call_idx : 0) * p.aff_call_stride;
+#pragma unroll
+  for (int u = 0; u < MAXP; ++u) {
+    if (rowc[u] >= 0) {
+      const int l = rowc[u] >> 16, c = rowc[u] & 0xffff;
+      const size_t gidx = ((size_t)b * L + l) * C + c;
+      float4 x = v[u];
+      if (p.raw) store_op4<KIND>(p.raw, gidx, x);
+      x.x = (x.x - mean) * rstd; x.y = (x.y - mean) * rstd; x.z = (x.z - mean) * rstd; x.w = (x.w - mean) * rstd;
+      if (aff) {
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(aff + c));
+        const float4 ha = __ldg(reinterpret_cast<const float4*>(aff + C + c));
+        x.x = x.x * ga.x + ha.x; x.y = x.y * ga.y + ha.y; x.z = x.z * ga.z + ha.z; x.w = x.w * ga.w + ha.w;
+      }
+      if (p.silu) { x.x = silu_f(x.x); x.y = silu_f(x.y); x.z = silu_f(x.z); x.w = silu_f(x.w); }
+      store_op4<KIND>(p.out, gidx, x);
+    }
+  }
+}
+
 static int gn_spc(int L, int C) {
   int spc = 4096 / (L * C);
   if (spc < 1) spc = 1;
@@ -132,6 +200,21 @@ bool gn_apply_supported(int L, int C, int groups) {
 cudaError_t launch_gn_apply(const GnApplyParams& p, int kind, cudaStream_t s) {
   if (p.B <= 0) return cudaSuccess;
   const int C = p.c0 + p.c1;
+  {
+    const int cpg = C / p.groups;
+    const int pieces = p.L * cpg / 4;                    // float4 per (sample, group)
+    if (cpg % 4 == 0 && pieces <= 256 && C < 65536 && p.L < 32768) {
+      int seg = 1;
+      while (seg < pieces && seg < 32) seg <<= 1;
+      const int gpw = 32 / seg;
+      const long long items = (long long)p.B * p.groups;
+      const long long warps = (items + gpw - 1) / gpw;
+      const unsigned grid = (unsigned)((warps + 7) / 8);
+      if (kind == 1) gn_apply_reg_kernel<1, 8><<<grid, 256, 0, s>>>(p, seg, pieces);
+      else gn_apply_reg_kernel<2, 8><<<grid, 256, 0, s>>>(p, seg, pieces);
+      return cudaGetLastError();
+    }
+  }
   const int spc = gn_spc(p.L, C);
   const size_t smem = ((size_t)spc * p.L * C + 2 * (size_t)spc * p.groups) * sizeof(float);
   const unsigned grid = (unsigned)((p.B + spc - 1) / spc);
