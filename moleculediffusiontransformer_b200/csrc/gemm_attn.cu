@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
         if (!p.cross) {
           attend_head_mma<1, KIND>(Qs + (size_t)s * L * A_LD, A_LD, Ks + (size_t)s * L * A_LD, Vs + (size_t)s * L * A_LD, A_LD, L, L,
                                    p.scale, p.att, ob, p.ldo, lane);
-        } else if (KIND == 1) {
+        } else if (KIND == 1 || p.kv_fp32) {
           // fp32-storage K/V cache: the copy for this item was issued one item ago with cp.async; issue the next one now
           if (!pf_primed) { issue_kv(t, s, pf_buf); pf_primed = true; }
           int nt = t, ns = s + s_step;

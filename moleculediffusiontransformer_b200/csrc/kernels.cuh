@@ -185,6 +185,7 @@ struct GemmAttnParams {
   void* att; int ldo;     // head outputs [M][heads * d] in the operand dtype
   const void* kc; const void* kn;  // cross: conditioning K|V cache [B][nk][2 * heads * d] and the shared null-branch block
   int ldkv; long long kv_sample_stride; int n_cond; int nk;
+  int kv_fp32;            // the cache pointers hold fp32 (always true in tf32 mode; bf16 mode may pass the fp32 cache)
 };
 bool gemm_attn_supported(int kind, int C, int L, int heads, int d, int cross, int nk_max);
 cudaError_t init_gemm_attn();

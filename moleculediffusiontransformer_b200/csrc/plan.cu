@@ -309,7 +309,7 @@ struct Builder {
     GemmAttnParams& g = op.gat;
     g.M = 0; g.heads = heads; g.d = d; g.kchunks = C / kch; g.C = C; g.L = L; g.Sb = 128 / L; g.cross = cross;
     g.bias = bias; g.scale = 1.0f / sqrtf((float)d); g.att = pl.att; g.ldo = heads * d;
-    g.kc = kc; g.kn = kn; g.ldkv = 2 * heads * d; g.kv_sample_stride = 0; g.n_cond = 0; g.nk = L;
+    g.kc = kc; g.kn = kn; g.ldkv = 2 * heads * d; g.kv_sample_stride = 0; g.n_cond = 0; g.nk = L; g.kv_fp32 = 1;
     const void* wop = tc_copy(dW32, (size_t)heads * BN * C);
     if (make_tmap_act(op.tmA, A, pl.prec, C, L, (long long)pl.Beff_max) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(attn activation) failed");
     if (make_tmap_weight(op.tmB, wop, pl.prec, (long long)C, heads * BN, BN) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(attn weight) failed");
@@ -520,7 +520,9 @@ struct Builder {
         const bool fuse_cross = fast && fuse_attn && gemm_attn_supported(pl.prec, C, L, heads, d, 1, pl.cfg.ctx_max_length);
         if (fuse_cross) {
           emit_ln_apply(prog, t, C, L, tn);
-          emit_gemm_attn(prog, tn, C, L, d_wq, d_bq, 1, layer, cl.kv_cond_op, cl.kv_null_op);
+          // the fused kernel streams fp32 K/V with cp.async in both tensor-core modes (tf32: rounded copy, bf16: the fp32 cache)
+          emit_gemm_attn(prog, tn, C, L, d_wq, d_bq, 1, layer, pl.prec == MDT_PREC_TF32 ? cl.kv_cond_op : (void*)cl.kv_cond,
+                         pl.prec == MDT_PREC_TF32 ? cl.kv_null_op : (void*)cl.kv_null);
         } else if (fast) {
           emit_ln_apply(prog, t, C, L, tn);
           emit_gemm_tma(prog, tn, C, L, 1, d_wq, d_bq, Hd, 0, nullptr, nullptr, pl.qc);

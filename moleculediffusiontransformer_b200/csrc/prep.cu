@@ -210,8 +210,11 @@ cudaError_t launch_gn_apply(const GnApplyParams& p, int kind, cudaStream_t s) {
       const long long items = (long long)p.B * p.groups;
       const long long warps = (items + gpw - 1) / gpw;
       const unsigned grid = (unsigned)((warps + 7) / 8);
-      if (kind == 1) gn_apply_reg_kernel<1, 8><<<grid, 256, 0, s>>>(p, seg, pieces);
-      else gn_apply_reg_kernel<2, 8><<<grid, 256, 0, s>>>(p, seg, pieces);
+      const int ppl = (pieces + seg - 1) / seg;          // float4 pieces per lane: sizes the register arrays
+#define MDT_GN_LAUNCH(K, P) gn_apply_reg_kernel<K, P><<<grid, 256, 0, s>>>(p, seg, pieces)
+      if (kind == 1) { if (ppl <= 1) MDT_GN_LAUNCH(1, 1); else if (ppl <= 2) MDT_GN_LAUNCH(1, 2); else if (ppl <= 4) MDT_GN_LAUNCH(1, 4); else MDT_GN_LAUNCH(1, 8); }
+      else { if (ppl <= 1) MDT_GN_LAUNCH(2, 1); else if (ppl <= 2) MDT_GN_LAUNCH(2, 2); else if (ppl <= 4) MDT_GN_LAUNCH(2, 4); else MDT_GN_LAUNCH(2, 8); }
+#undef MDT_GN_LAUNCH
       return cudaGetLastError();
     }
   }
@@ -223,24 +226,24 @@ cudaError_t launch_gn_apply(const GnApplyParams& p, int kind, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-template <int KIND>
+template <int KIND, int NV>   // NV = float4 per lane = C / 128 rounded up (register array size)
 __global__ void __launch_bounds__(256) ln_apply_kernel(const LnApplyParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + warp;
   if (row >= p.rows) return;
   const int C = p.C;
   const float* src = p.src + (size_t)row * C;
-  float4 v[8];  // C <= 1024
+  float4 v[NV];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = i * 128 + lane * 4;
     if (c < C) { v[i] = __ldg(reinterpret_cast<const float4*>(src + c)); sum += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
   }
   const float mean = warp_sum_f(sum) / (float)C;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = i * 128 + lane * 4;
     if (c < C) {
       const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(256) ln_apply_kernel(const LnApplyParams p) {
   }
   const float rstd = 1.0f / sqrtf(warp_sum_f(sq) / (float)C + p.eps);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = i * 128 + lane * 4;
     if (c < C) {
       float4 o = make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd);
@@ -262,8 +265,11 @@ cudaError_t launch_ln_apply(const LnApplyParams& p, int kind, cudaStream_t s) {
   if (p.rows <= 0) return cudaSuccess;
   if (p.C % 4 || p.C > 1024) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)((p.rows + 7) / 8);
-  if (kind == 1) ln_apply_kernel<1><<<grid, 256, 0, s>>>(p);
-  else ln_apply_kernel<2><<<grid, 256, 0, s>>>(p);
+  const int nv = (p.C + 127) / 128;
+#define MDT_LN_LAUNCH(K, N) ln_apply_kernel<K, N><<<grid, 256, 0, s>>>(p)
+  if (kind == 1) { if (nv <= 1) MDT_LN_LAUNCH(1, 1); else if (nv <= 2) MDT_LN_LAUNCH(1, 2); else if (nv <= 4) MDT_LN_LAUNCH(1, 4); else MDT_LN_LAUNCH(1, 8); }
+  else { if (nv <= 1) MDT_LN_LAUNCH(2, 1); else if (nv <= 2) MDT_LN_LAUNCH(2, 2); else if (nv <= 4) MDT_LN_LAUNCH(2, 4); else MDT_LN_LAUNCH(2, 8); }
+#undef MDT_LN_LAUNCH
   return cudaGetLastError();
 }
 
