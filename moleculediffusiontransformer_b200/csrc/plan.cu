@@ -55,7 +55,7 @@ struct MdtError {
 // ------------------------------------------------------------------------------------------------
 // program representation
 // ------------------------------------------------------------------------------------------------
-enum OpType { OP_GEMM, OP_GN_STATS, OP_ROW_STATS, OP_ATTN, OP_UPGATHER, OP_PERMUTE, OP_GN_APPLY, OP_LN_APPLY, OP_GEMM_TMA, OP_GEMM_ATTN };
+enum OpType { OP_GEMM, OP_GN_STATS, OP_ROW_STATS, OP_ATTN, OP_UPGATHER, OP_PERMUTE, OP_GN_APPLY, OP_LN_APPLY, OP_GEMM_TMA, OP_GEMM_ATTN, OP_DUP_ROWS };
 
 struct Op {
   OpType type = OP_GEMM;
@@ -79,7 +79,9 @@ struct Op {
   std::string tap;
   const float* tap_ptr = nullptr;
   int tap_rps = 0, tap_c = 0;
-  bool per_sample_fixed = false;  // op independent of batch (time / null-context programs use explicit M)
+  // classifier-free guidance: ops ahead of the first cross-attention see identical inputs in the conditional and the
+  // null branch (modules.py:1250-1251 call the same x, time), so they run on the conditional rows only
+  bool half = false;
 };
 
 struct Film {   // one ResnetBlock1d's FiLM table
@@ -240,7 +242,23 @@ struct Builder {
     a.call_idx = nullptr; a.silu = 0;
     return a;
   }
-  Op& emit(std::vector<Op>& prog, const Op& op) { prog.push_back(op); return prog.back(); }
+  // ---- shared classifier-free-guidance prefix bookkeeping
+  bool prefix = true;                      // ops emitted while true run on the conditional rows only
+  struct Keep { float* p; int rps; int C; };
+  std::vector<Keep> prefix_keep;           // fp32 tensors produced in the prefix that are read after it (skips)
+  Op& emit(std::vector<Op>& prog, const Op& op) { prog.push_back(op); prog.back().half = prefix; return prog.back(); }
+  // end of the prefix: replicate every live tensor into the null-branch rows, then continue on all rows
+  void end_prefix(std::vector<Op>& prog, float* live, int rps, int C) {
+    if (!prefix) return;
+    prefix = false;
+    auto dup = [&](float* ptr, int r, int c) {
+      Op op; op.type = OP_DUP_ROWS; op.out = ptr; op.i0 = r; op.i1 = c;
+      prog.push_back(op);
+    };
+    if (live) dup(live, rps, C);
+    for (const Keep& k : prefix_keep) if (k.p != live) dup(k.p, k.rps, k.C);
+    prefix_keep.clear();
+  }
 
   Op gemm_op(const ALoad& a, const float* dW, const void* dWtc, const float* dbias, int N, int act, const float* res,
              float* out, int rps) {
@@ -501,6 +519,7 @@ struct Builder {
       // ---- cross attention onto the conditioning embedding (K/V are loop invariant: precomputed per sample)
       if (has_cross) {
         if (!with_ctx) raise(MDT_ERR_INVALID, "unexpected cross_attention under '%s'", bp.c_str());
+        end_prefix(prog, t, L, C);   // the branches diverge here (different K/V)
         const std::string ap = bp + "cross_attention.";
         std::vector<float> wq(T(ap + "to_q.weight", (int64_t)Hd * C), T(ap + "to_q.weight", (int64_t)Hd * C) + (size_t)Hd * C), bq(Hd, 0.f);
         fold_affine(wq, bq, Hd, C, T(ap + "norm.weight", C), T(ap + "norm.bias", C));
@@ -668,6 +687,7 @@ struct Builder {
     }
     set_tap(prog, "to_in", cur, Ll[0], Cl[0]);
     const float* skip0 = cur;  // held until the end
+    if (prefix) prefix_keep.push_back({cur, Ll[0], Cl[0]});
     std::vector<std::vector<const float*>> skips(nlev);
     const float* xcur = cur;
     bool xcur_owned = false;   // skip0 must not be released
@@ -711,6 +731,7 @@ struct Builder {
         // previous xcur: release unless it is a stored skip
         if (j == 0) release(xcur);
         skips[i].push_back(r);
+        if (prefix) prefix_keep.push_back({r, Lo, Co});
         xcur = r;
       }
       const bool more_levels = (i + 1 < nlev);
@@ -721,6 +742,7 @@ struct Builder {
         xcur = t;
       }
       xcur_owned = false;  // xcur is a stored skip now
+      if (prefix) end_prefix(prog, const_cast<float*>(xcur), Lo, Co);
       if (c.num_blocks[i] == 0 && c.attentions[i] == 0) raise(MDT_ERR_INVALID, "level without blocks unsupported");
     }
     {
@@ -817,8 +839,19 @@ static void launch_gemm(mdt_plan& pl, const GemmParams& g, cudaStream_t s) {
 }
 
 static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_cond, int n_ctx, cudaStream_t s) {
+  if (getenv("MDT_NO_SHARED_PREFIX")) for (Op& op : prog) op.half = false;
+  const int Beff_full = Beff;
   for (Op& op : prog) {
+    Beff = op.half ? n_cond : Beff_full;
     switch (op.type) {
+      case OP_DUP_ROWS: {
+        if (Beff_full > n_cond) {
+          const size_t n = (size_t)n_cond * op.i0 * op.i1;
+          CK(cudaMemcpyAsync(op.out + n, op.out, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+          pl.launches++;
+        }
+        break;
+      }
       case OP_GEMM: { GemmParams g = op.g; g.M = Beff * op.rps; launch_gemm(pl, g, s); break; }
       case OP_GN_STATS: { NormStatsParams n = op.ns; n.rows = Beff; CK(launch_groupnorm_stats(n, s)); pl.launches++; break; }
       case OP_ROW_STATS: { NormStatsParams n = op.ns; n.rows = Beff * op.rps; CK(launch_rownorm_stats(n, s)); pl.launches++; break; }
