@@ -34,13 +34,15 @@ template <int KIND>  // 1 = tf32 (32 elements per 128-byte chunk), 2 = bf16 (64 
 __global__ void __launch_bounds__(160) gemm_tc_kernel(const GemmParams p, const int BN, const uint32_t idesc, const int num_chunks) {
   constexpr int KCH = (KIND == 1) ? 32 : 64;
   constexpr int ESZ = (KIND == 1) ? 4 : 2;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B operand tiles need 1024-byte alignment
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_base_s;
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // keep the pointer in the shared address space (an integer round trip would demote every access to generic LD/ST)
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * BN;
   const uint32_t tmem_cols = BN <= 32 ? 32u : (BN <= 64 ? 64u : 128u);

@@ -39,14 +39,16 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const TmaGemmParams p, const uint32_t idesc) {
   constexpr int KCH = (KIND == 1) ? 32 : 64;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B operand tiles need 1024-byte alignment
   __shared__ __align__(8) uint64_t full_bar[T_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[T_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // keep the pointer in the shared address space (an integer round trip would demote every access to generic LD/ST)
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = p.BN;
   const int n_tiles = p.N / BN;
