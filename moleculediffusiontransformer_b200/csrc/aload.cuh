@@ -7,6 +7,20 @@ namespace mdt {
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }                 // nn.SiLU
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }  // nn.GELU() (erf form)
 
+// exact-erf GELU evaluated with the Abramowitz-Stegun 7.1.26 rational form (|erf error| <= 1.5e-7, i.e. fp32 rounding level):
+// one MUFU.EX2, one MUFU.RCP and a degree-5 Horner instead of the ~30-instruction erff.  Used only where the result is
+// rounded to tf32 / bf16 right away (tensor-core modes); the fp32 mode keeps erff.
+__device__ __forceinline__ float gelu_as(float v) {
+  const float x = fabsf(v) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-x * x);          // erf(|v| / sqrt(2))
+  return 0.5f * v * (1.0f + copysignf(e, v));
+}
+
 __device__ __forceinline__ const float* aload_aff(const ALoad& a) {
   if (!a.aff) return nullptr;
   int call = a.call_idx ? *a.call_idx : 0;

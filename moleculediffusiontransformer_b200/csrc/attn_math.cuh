@@ -138,9 +138,12 @@ __device__ __forceinline__ void attend_head_mma_nt(const typename SmemIO<SK>::T*
   const int g = lane >> 2, q = lane & 3;
   for (int i0 = 0; i0 < nq; i0 += 16) {
     const int r0 = min(i0 + g, nq - 1), r1 = min(i0 + g + 8, nq - 1);
-    float sc[NT][4];
+    float sc[NT][4], sd[NT][4];   // two accumulator sets (even / odd k-steps): halves the dependent MMA chain
 #pragma unroll
-    for (int t = 0; t < NT; ++t) { sc[t][0] = 0.f; sc[t][1] = 0.f; sc[t][2] = 0.f; sc[t][3] = 0.f; }
+    for (int t = 0; t < NT; ++t) {
+      sc[t][0] = 0.f; sc[t][1] = 0.f; sc[t][2] = 0.f; sc[t][3] = 0.f;
+      sd[t][0] = 0.f; sd[t][1] = 0.f; sd[t][2] = 0.f; sd[t][3] = 0.f;
+    }
     int jr[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) jr[t] = min(t * 8 + g, nk - 1) * sb;
@@ -155,9 +158,12 @@ __device__ __forceinline__ void attend_head_mma_nt(const typename SmemIO<SK>::T*
       for (int t = 0; t < NT; ++t) {
         const uint32_t b0 = __float_as_uint(IO::ld1(ks + jr[t] + k0 + q));
         const uint32_t b1 = __float_as_uint(IO::ld1(ks + jr[t] + k0 + q + 4));
-        mma_tf32_16x8x8(sc[t], a, b0, b1);
+        if ((k0 >> 3) & 1) mma_tf32_16x8x8(sd[t], a, b0, b1);
+        else mma_tf32_16x8x8(sc[t], a, b0, b1);
       }
     }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) { sc[t][0] += sd[t][0]; sc[t][1] += sd[t][1]; sc[t][2] += sd[t][2]; sc[t][3] += sd[t][3]; }
     // softmax over keys: thread holds columns 8t + 2q, 8t + 2q + 1 of rows g (c0, c1) and g + 8 (c2, c3)
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
                 const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + no));
                 o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
               }
-              if (p.act == 1) { o.x = gelu_f(o.x); o.y = gelu_f(o.y); o.z = gelu_f(o.z); o.w = gelu_f(o.w); }
+              if (p.act == 1) { o.x = gelu_as(o.x); o.y = gelu_as(o.y); o.z = gelu_as(o.z); o.w = gelu_as(o.w); }
               if (p.res) {
                 const float4 rv = *reinterpret_cast<const float4*>(p.res + (size_t)mo * p.ldres + no);
                 o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;

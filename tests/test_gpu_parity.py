@@ -98,6 +98,26 @@ def test_chunking_and_graph_replay_are_invisible(model_cache, monkeypatch):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_shared_cfg_prefix_is_exact(prec, model_cache, monkeypatch):
+    """Ops ahead of the first cross-attention run once on the conditional rows and are replicated to the null rows
+    (modules.py:1250-1251 feed both branches the same x, time): bit-identical to running them on both halves."""
+    from moleculediffusiontransformer_b200 import ADPM2Sampler, KarrasSchedule
+    from moleculediffusiontransformer_b200.plan import SamplerPlan
+
+    m = model_cache("inverse", INV64, 0)
+    seq, noise0, step_noise = make_inputs("inv64_short_ctx_clamp")
+    kw = dict(num_steps=8, sigma_schedule=KarrasSchedule(0.001, 9.0, 3.0), sampler=ADPM2Sampler(1.0), clamp=False, cond_scale=3.0)
+    outs = []
+    for flag in (None, "1"):
+        if flag:
+            monkeypatch.setenv("MDT_NO_SHARED_PREFIX", flag)
+        plan = SamplerPlan(m, "cuda:0", precision=prec, max_batch=8)
+        outs.append(plan.sample(seq, noise0=noise0, step_noise=step_noise, **kw).cpu())
+        plan.close()
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_philox_noise_is_sharding_invariant_and_deterministic(model_cache):
     from moleculediffusiontransformer_b200 import ADPM2Sampler, KarrasSchedule
     from moleculediffusiontransformer_b200.plan import SamplerPlan
