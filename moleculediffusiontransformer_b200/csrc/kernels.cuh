@@ -191,6 +191,20 @@ bool gemm_attn_supported(int kind, int C, int L, int heads, int d, int cross, in
 cudaError_t init_gemm_attn();
 cudaError_t launch_gemm_attn(const void* tmA, const void* tmB, const GemmAttnParams& p, int kind, cudaStream_t s);
 
+// ---- fused FeedForward (gemm_ff.cu): Linear -> GELU -> Linear + residual, hidden activation stays on chip ---------
+struct GemmFFParams {
+  int M, C, mid;          // rows, model width, hidden width (mid = C * multiplier)
+  int L, Sb;              // positions per sample; samples per 128-row tile (TMA box of the activation map)
+  const float* b0;        // [mid]
+  const float* b2;        // [C]
+  const float* res;       // residual stream [M][C] fp32 (may alias out)
+  float* out;             // [M][C] fp32
+  void* out_op;           // optional operand-dtype copy of out
+};
+bool gemm_ff_supported(int kind, int C, int mid, int L);
+cudaError_t init_gemm_ff();
+cudaError_t launch_gemm_ff(const void* tmA, const void* tmW0, const void* tmW2, const GemmFFParams& p, int kind, cudaStream_t s);
+
 // ---- tensor-core GEMM (gemm_tc.cu) --------------------------------------------------------------
 // kind: 1 = tf32, 2 = bf16.  Wtc must hold the weights pre-converted by convert_weights_tc().
 cudaError_t launch_gemm_tc(const GemmParams& p, int kind, cudaStream_t s);

@@ -55,7 +55,7 @@ struct MdtError {
 // ------------------------------------------------------------------------------------------------
 // program representation
 // ------------------------------------------------------------------------------------------------
-enum OpType { OP_GEMM, OP_GN_STATS, OP_ROW_STATS, OP_ATTN, OP_UPGATHER, OP_PERMUTE, OP_GN_APPLY, OP_LN_APPLY, OP_GEMM_TMA, OP_GEMM_ATTN, OP_DUP_ROWS };
+enum OpType { OP_GEMM, OP_GN_STATS, OP_ROW_STATS, OP_ATTN, OP_UPGATHER, OP_PERMUTE, OP_GN_APPLY, OP_LN_APPLY, OP_GEMM_TMA, OP_GEMM_ATTN, OP_DUP_ROWS, OP_GEMM_FF };
 
 struct Op {
   OpType type = OP_GEMM;
@@ -68,8 +68,10 @@ struct Op {
   LnApplyParams la{};
   TmaGemmParams tg{};
   GemmAttnParams gat{};
+  GemmFFParams gff{};
   alignas(64) unsigned char tmA[128];
   alignas(64) unsigned char tmB[128];
+  alignas(64) unsigned char tmC[128];
   bool cross = false;  // attention reads the precomputed conditioning K/V
   int cross_layer = -1;
   // upsample gather / permute
@@ -315,6 +317,20 @@ struct Builder {
     const void* wop = tc_copy(dW32, (size_t)N * taps * C);
     if (make_tmap_act(op.tmA, A, pl.prec, C, L, (long long)pl.Beff_max) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(activation C=%d L=%d) failed", C, L);
     if (make_tmap_weight(op.tmB, wop, pl.prec, (long long)taps * C, N, g.BN) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(weight K=%d N=%d) failed", taps * C, N);
+    emit(prog, op);
+  }
+
+  // fused FeedForward (gemm_ff.cu): x_op -> GELU(x W0^T + b0) W2^T + b2 + res, hidden activation never leaves the SM
+  void emit_gemm_ff(std::vector<Op>& prog, const void* xop, int C, int mid, int L, const float* dW0, const float* b0,
+                    const float* dW2, const float* b2, float* t, void* out_op) {
+    Op op; op.type = OP_GEMM_FF; op.rps = L;
+    GemmFFParams& g = op.gff;
+    g.M = 0; g.C = C; g.mid = mid; g.L = L; g.Sb = 128 / L; g.b0 = b0; g.b2 = b2; g.res = t; g.out = t; g.out_op = out_op;
+    const void* w0 = tc_copy(dW0, (size_t)mid * C);
+    const void* w2 = tc_copy(dW2, (size_t)C * mid);
+    if (make_tmap_act(op.tmA, xop, pl.prec, C, L, (long long)pl.Beff_max) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(ff activation) failed");
+    if (make_tmap_weight(op.tmB, w0, pl.prec, (long long)C, mid, 64) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(ff W0) failed");
+    if (make_tmap_weight(op.tmC, w2, pl.prec, (long long)mid, C, C) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(ff W2) failed");
     emit(prog, op);
   }
 
@@ -577,7 +593,11 @@ struct Builder {
         const float* d_b0 = upload(T(bp + "feed_forward.0.bias", mid), mid);
         const float* d_w2 = upload(T(bp + "feed_forward.2.weight", (int64_t)C * mid), (size_t)C * mid);
         const float* d_b2 = upload(T(bp + "feed_forward.2.bias", C), C);
-        if (fast) {
+        // The chained FF kernel keeps the hidden activation on chip but serialises the two GEMMs per 128-row block; on B200 it
+        // measured slower (125 us vs 103 us per level-1 layer, profiles/README.md) than two persistent GEMMs, so it is opt-in.
+        if (fast && getenv("MDT_FUSED_FF") && gemm_ff_supported(pl.prec, C, mid, L)) {
+          emit_gemm_ff(prog, tn, C, mid, L, d_w0, d_b0, d_w2, d_b2, t, (i == nblocks - 1) ? (void*)tn : nullptr);
+        } else if (fast) {
           emit_gemm_tma(prog, tn, C, L, 1, d_w0, d_b0, mid, 1, nullptr, nullptr, pl.ff);
           // the last block's output is consumed by to_out as a raw operand: write the copy here
           emit_gemm_tma(prog, pl.ff, mid, L, 1, d_w2, d_b2, C, 0, t, t, (i == nblocks - 1) ? (void*)tn : nullptr);
@@ -867,6 +887,7 @@ static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_con
         if (op.cross) { g.nk = n_ctx; g.kv_sample_stride = (long long)n_ctx * g.ldkv; g.n_cond = n_cond; }
         CK(launch_gemm_attn(op.tmA, op.tmB, g, pl.prec, s)); pl.launches++; break;
       }
+      case OP_GEMM_FF: { GemmFFParams g = op.gff; g.M = Beff * op.rps; CK(launch_gemm_ff(op.tmA, op.tmB, op.tmC, g, pl.prec, s)); pl.launches++; break; }
       case OP_GEMM_TMA: { TmaGemmParams g = op.tg; g.M = Beff * op.rps; CK(launch_gemm_tma(op.tmA, op.tmB, g, pl.prec, s)); pl.launches++; break; }
       case OP_UPGATHER: CK(launch_upsample_gather(op.in0, op.in1, op.in2, op.out, Beff, op.i0, op.i1, op.i2, s)); pl.launches++; break;
       case OP_PERMUTE: CK(launch_patch_permute(op.in0, op.out, Beff, op.i0, op.i1, op.i2, op.i3, s)); pl.launches++; break;
@@ -1018,6 +1039,7 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
     CK(init_gemm_tc());
     CK(init_gemm_tma());
     CK(init_gemm_attn());
+    CK(init_gemm_ff());
     pl->cfg = *cfg; pl->device = device; pl->prec = cfg->precision;
     pl->P = cfg->in_channels; pl->L0 = cfg->length; pl->Hd = cfg->heads * cfg->head_features; pl->F = cfg->ctx_features;
     pl->Bmax = cfg->max_batch; pl->Beff_max = 2 * cfg->max_batch;
