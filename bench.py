@@ -180,7 +180,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = mdt.QMDiffusion(**MODEL_KW).eval()
     B = args.batch
-    plan = model._plan_for(dev, args.precision)
+    plan = model._plan_for(dev, args.precision, batch=B)
     sched, sampler = KarrasSchedule(0.001, 9.0, 3.0), ADPM2Sampler(1.0)
     cond_host = make_cond(B, offset=rank).pin_memory()
     cond_dev = cond_host.to(dev)
@@ -260,7 +260,7 @@ def run_ours(args):
     }
     if args.also and args.also != args.precision:
         # secondary arithmetic mode, same workload, device-resident timing only (reported beside the headline)
-        plan2 = model._plan_for(dev, args.also)
+        plan2 = model._plan_for(dev, args.also, batch=B)
         def step2(i):
             return plan2.sample(cond_dev, num_steps=TIMESTEPS, sigma_schedule=sched, sampler=sampler, clamp=False,
                                 cond_scale=COND_SCALE, seed=1234 + i, sample_offset=rank * B, return_tokens=True)

@@ -142,6 +142,71 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0 + cc), v);
           const int ncol = min(32, cols_per_half - cc);
+          if (p.gn_L > 0) {
+            // ---- fused GroupNorm of (acc + bias): statistics over gn_L rows (lanes) x gn_cpg columns, all inside this block
+            const int nb0 = nt * BN + col0 + cc;
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb0 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              x[4 * j] = __uint_as_float(v[4 * j]) + bv.x; x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv.y;
+              x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv.z; x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv.w;
+            }
+            const float inv_n = 1.0f / (float)(p.gn_L * p.gn_cpg);
+            if (p.gn_cpg == 32) {
+              float s = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s += x[j];
+              for (int o = p.gn_L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+              const float mean = s * inv_n;
+              float sq = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { const float d = x[j] - mean; sq = fmaf(d, d, sq); }
+              for (int o = p.gn_L >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+              const float rstd = 1.0f / sqrtf(sq * inv_n + p.gn_eps);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = (x[j] - mean) * rstd;
+            } else {  // gn_cpg == 16: two groups per 32-column block
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { s0 += x[j]; s1 += x[16 + j]; }
+              for (int o = p.gn_L >> 1; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+              const float m0 = s0 * inv_n, m1 = s1 * inv_n;
+              float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { const float d0 = x[j] - m0, d1 = x[16 + j] - m1; q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); }
+              for (int o = p.gn_L >> 1; o > 0; o >>= 1) { q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
+              const float r0 = 1.0f / sqrtf(q0 * inv_n + p.gn_eps), r1 = 1.0f / sqrtf(q1 * inv_n + p.gn_eps);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { x[j] = (x[j] - m0) * r0; x[16 + j] = (x[16 + j] - m1) * r1; }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(stg + lane * T_STG_LD + j * 4) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            __syncwarp();
+            const int cl = (lane & 7) * 4;
+            const float* aff = p.gn_aff + (size_t)(p.gn_call ? *p.gn_call : 0) * p.gn_aff_stride;
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(aff + nb0 + cl));
+            const float4 gb = __ldg(reinterpret_cast<const float4*>(aff + p.N + nb0 + cl));
+#pragma unroll
+            for (int rr = lane >> 3; rr < 32; rr += 4) {
+              const int mo = mt * T_TM + q * 32 + rr, no = nb0 + cl;
+              if (mo < p.M) {
+                float4 o = *reinterpret_cast<const float4*>(stg + rr * T_STG_LD + cl);
+                o.x = fmaf(o.x, ga.x, gb.x); o.y = fmaf(o.y, ga.y, gb.y); o.z = fmaf(o.z, ga.z, gb.z); o.w = fmaf(o.w, ga.w, gb.w);
+                o.x = o.x * __fdividef(1.0f, 1.0f + __expf(-o.x)); o.y = o.y * __fdividef(1.0f, 1.0f + __expf(-o.y));
+                o.z = o.z * __fdividef(1.0f, 1.0f + __expf(-o.z)); o.w = o.w * __fdividef(1.0f, 1.0f + __expf(-o.w));
+                if (KIND == 1)
+                  *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.Cop) + (size_t)mo * p.ldcop + no) =
+                      make_uint4(to_tf32(o.x), to_tf32(o.y), to_tf32(o.z), to_tf32(o.w));
+                else
+                  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.Cop) + (size_t)mo * p.ldcop + no) =
+                      make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+              }
+            }
+            __syncwarp();
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(stg + lane * T_STG_LD + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);

@@ -164,6 +164,10 @@ struct TmaGemmParams {
   const float* res; int ldres;
   float* C32; int ldc;        // fp32 output (residual stream) or null
   void* Cop; int ldcop;       // operand-dtype copy of the same values (next GEMM / attention input) or null
+  // optional fused GroupNorm (+ per-call affine with FiLM folded in + SiLU) of the biased output, written to Cop only:
+  // a 32-row x 32-column epilogue block holds whole (sample, group) sets when gn_L | 32 and gn_cpg | 32 (gn_L = 0: off)
+  int gn_L, gn_cpg; float gn_eps;
+  const float* gn_aff; int gn_aff_stride; const int* gn_call;
 };
 // 128-byte CUtensorMap blobs (64-byte aligned) built on the host
 int make_tmap_act(void* map128, const void* base, int kind, int C, int L, long long samples);

@@ -367,19 +367,30 @@ struct Builder {
     const bool ok1 = tma_ok(Cin, L, Cout) && gn_apply_supported(L, Cin, groups);
     const bool ok2 = tma_ok(Cout, L, Cout) && gn_apply_supported(L, Cout, groups);
     const bool proj = has(pre + "to_out.weight");
-    float* h1 = acquire();
-    float* a1 = nullptr; float* raw = nullptr;
+    // block2's GroupNorm + FiLM + SiLU can run inside conv1's epilogue when a 32-row x 32-column epilogue block holds
+    // whole (sample, group) sets: then h1 never goes to HBM and the separate normalisation pass disappears
+    const int cpg2 = Cout / groups;
+    const bool fuse_gn = ok1 && ok2 && !getenv("MDT_NO_FUSED_GN") && tma_pick_bn(Cout) == 128 && L <= 32 && (32 % L) == 0 &&
+                         (cpg2 == 16 || cpg2 == 32);
+    float* h1 = fuse_gn ? nullptr : acquire();
+    float* a1 = nullptr; float* raw = nullptr; float* a2f = nullptr;
     if (ok1) {
       a1 = acquire();
       if (proj) raw = acquire();
       emit_gn_apply(prog, in, L, groups, 1e-5f, d_aff1, 0, nullptr, 1, a1, raw);
-      emit_gemm_tma(prog, a1, Cin, L, 3, d_w1, d_b1, Cout, 0, nullptr, h1, nullptr);
+      if (fuse_gn) {
+        a2f = acquire();
+        emit_gemm_tma(prog, a1, Cin, L, 3, d_w1, d_b1, Cout, 0, nullptr, nullptr, a2f);   // gn_* fields are patched below
+      } else {
+        emit_gemm_tma(prog, a1, Cin, L, 3, d_w1, d_b1, Cout, 0, nullptr, h1, nullptr);
+      }
     } else {
       gn_stats(prog, in, L, groups, 1e-5f);
       ALoad a = make_aload(in, L, L, 3, 1, 1);
       a.stats = pl.gn_stats; a.stats_mode = 2; a.groups = groups; a.cpg = Cin / groups; a.aff = d_aff1; a.silu = 1;
       emit(prog, gemm_op(a, d_w1, tc_copy(d_w1, w1.size()), d_b1, Cout, 0, nullptr, h1, L));
     }
+    const size_t conv1_index = prog.size() - 1;
     // FiLM table of this block
     Film f{};
     f.w_ss = upload(T(pre + "to_scale_shift.to_scale_shift.1.weight", (int64_t)2 * Cout * M), (size_t)2 * Cout * M);
@@ -390,6 +401,10 @@ struct Builder {
     f.ss = dalloc((size_t)pl.max_calls * 2 * Cout);
     f.aff = dalloc((size_t)pl.max_calls * 2 * Cout);
     pl.films.push_back(f);
+    if (fuse_gn) {
+      TmaGemmParams& g1 = prog[conv1_index].tg;
+      g1.gn_L = L; g1.gn_cpg = cpg2; g1.gn_eps = 1e-5f; g1.gn_aff = f.aff; g1.gn_aff_stride = 2 * Cout; g1.gn_call = pl.d_call;
+    }
     // residual path
     float* out = forced_out ? forced_out : acquire();
     const float* res;
@@ -412,7 +427,12 @@ struct Builder {
     auto w2 = pack_conv(T(pre + "block2.project.weight", (int64_t)Cout * Cout * 3), Cout, Cout, 3);
     const float* d_w2 = upload(w2);
     const float* d_b2 = upload(T(pre + "block2.project.bias", Cout), Cout);
-    if (ok2) {
+    if (fuse_gn) {
+      void* oc = nullptr;
+      if (out_op) { oc = acquire(); *out_op = oc; }
+      emit_gemm_tma(prog, a2f, Cout, L, 3, d_w2, d_b2, Cout, 0, res, out, oc);
+      release(a2f);
+    } else if (ok2) {
       float* a2 = a1 ? a1 : acquire();   // a1 is dead once conv1 has run
       emit_gn_apply(prog, hs, L, groups, 1e-5f, f.aff, 2 * Cout, pl.d_call, 1, a2, nullptr);
       void* oc = nullptr;
@@ -428,7 +448,7 @@ struct Builder {
     }
     if (a1) release(a1);
     if (raw) release(raw);
-    release(h1);
+    if (h1) release(h1);
     return out;
   }
 

@@ -66,17 +66,21 @@ class _QMBase(nn.Module):
         self._plans = {}
 
     # ------------------------------------------------------------------ plan management
-    def _plan_for(self, device: torch.device, precision: Optional[str] = None):
-        from .plan import SamplerPlan, default_precision
+    def _plan_for(self, device: torch.device, precision: Optional[str] = None, batch: Optional[int] = None):
+        """One cached plan per (device, precision).  The workspace is sized for a power-of-two chunk that covers `batch`
+        (capped at MDT_MAX_BATCH, default 4096); a larger request rebuilds the plan, a smaller one reuses it."""
+        from .plan import SamplerPlan, default_max_batch, default_precision
 
         precision = precision or default_precision()
         key = (str(device), precision)
         plan = self._plans.get(key)
         version = sum(p._version for p in self.parameters())
-        if plan is None or plan.weights_version != version:
+        cap = default_max_batch()
+        want = cap if batch is None else min(cap, max(8, 1 << (max(int(batch), 1) - 1).bit_length()))
+        if plan is None or plan.weights_version != version or plan.max_batch < want:
             if plan is not None:
                 plan.close()
-            plan = SamplerPlan(self, device, precision=precision)
+            plan = SamplerPlan(self, device, precision=precision, max_batch=want)
             plan.weights_version = version
             self._plans[key] = plan
         return plan
@@ -104,7 +108,7 @@ class _QMBase(nn.Module):
             raise NotImplementedError(
                 "the accelerated path encodes the conditioning on the device; call model.sample(sequences, ...)")
         device = noise.device if noise is not None else sequences.device
-        plan = self._plan_for(torch.device(device), precision)
+        plan = self._plan_for(torch.device(device), precision, batch=sequences.shape[0])
         return plan.sample(sequences, noise0=noise, step_noise=step_noise, num_steps=num_steps,
                            sigma_schedule=sigma_schedule, sampler=sampler, clamp=clamp,
                            cond_scale=float(embedding_scale), seed=seed, return_tokens=return_tokens)

@@ -61,7 +61,7 @@ def model_runner(model, device, cond_scale: float, timesteps: int, seed: int, pr
     """run_shard closure over a QMDiffusion / QMDiffusionForward: returns uint8 tokens [rows, L]."""
 
     def run(rows: torch.Tensor, offset: int) -> torch.Tensor:
-        plan = model._plan_for(torch.device(device), precision)
+        plan = model._plan_for(torch.device(device), precision, batch=rows.shape[0])
         from .diffusion import ADPM2Sampler, KarrasSchedule
 
         _, tokens = plan.sample(rows, num_steps=timesteps, sigma_schedule=KarrasSchedule(0.001, 9.0, 3.0),

@@ -142,6 +142,17 @@ def test_philox_noise_is_sharding_invariant_and_deterministic(model_cache):
     assert torch.isfinite(z).all() and 0.01 < float(z.std()) < 10
 
 
+def test_launcher_single_process_matches_direct_call(model_cache):
+    from moleculediffusiontransformer_b200.launcher import model_runner, sharded_sample
+
+    m = model_cache("inverse", INV64, 0)
+    g = torch.Generator().manual_seed(9)
+    seq = torch.rand(5, 12, generator=g) * 2 - 1
+    tok = sharded_sample(model_runner(m, "cuda:0", 5.0, 6, seed=11, precision="tf32"), seq)
+    out, want = m.sample(seq, "cuda:0", cond_scale=5.0, timesteps=6, seed=11, precision="tf32", return_tokens=True)
+    assert tok.dtype == torch.uint8 and tok.shape == (5, 64) and torch.equal(tok, want)
+
+
 def test_reference_error_behaviour(model_cache):
     m = model_cache("inverse", INV64, 0)
     with pytest.raises(AssertionError):                                  # modules.py:1194-1195
