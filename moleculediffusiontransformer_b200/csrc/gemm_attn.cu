@@ -21,6 +21,12 @@ constexpr int A_STAGES = 2;
 constexpr int A_ABYTES = A_TM * 128;
 constexpr int A_EPI_WARPS = 8;
 constexpr int A_THREADS = 64 + 32 * A_EPI_WARPS;
+#ifndef MDT_ATTN_SKIP_MATH
+#define MDT_ATTN_SKIP_MATH 0
+#endif
+#ifndef MDT_ATTN_TRUNC
+#define MDT_ATTN_TRUNC 0
+#endif
 constexpr int A_LD = 68;   // staged q/k/v row stride in floats (64 + 4: conflict-free fragment loads)
 
 template <int KIND>
@@ -166,10 +172,14 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(dst + j * 4) =
-                make_uint4(to_tf32(__uint_as_float(v[4 * j])), to_tf32(__uint_as_float(v[4 * j + 1])),
-                           to_tf32(__uint_as_float(v[4 * j + 2])), to_tf32(__uint_as_float(v[4 * j + 3])));
+          for (int j = 0; j < 8; ++j) {
+            if (MDT_ATTN_TRUNC)   // experiment: let mma.sync truncate k / v to tf32 instead of rounding to nearest here
+              *reinterpret_cast<uint4*>(dst + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            else
+              *reinterpret_cast<uint4*>(dst + j * 4) =
+                  make_uint4(to_tf32(__uint_as_float(v[4 * j])), to_tf32(__uint_as_float(v[4 * j + 1])),
+                             to_tf32(__uint_as_float(v[4 * j + 2])), to_tf32(__uint_as_float(v[4 * j + 3])));
+          }
         }
       }
       tc_fence_before();
@@ -182,7 +192,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
         const int mrow = m0 + s * L;
         if (mrow >= p.M) break;
         const size_t ob = (size_t)mrow * p.ldo + (size_t)h * p.d;
-        if (!p.cross) {
+        if (MDT_ATTN_SKIP_MATH) {
+        } else if (!p.cross) {
           attend_head_mma<1, KIND>(Qs + (size_t)s * L * A_LD, A_LD, Ks + (size_t)s * L * A_LD, Vs + (size_t)s * L * A_LD, A_LD, L, L,
                                    p.scale, p.att, ob, p.ldo, lane);
         } else if (KIND == 1 || p.kv_fp32) {
