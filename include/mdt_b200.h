@@ -132,6 +132,18 @@ int mdt_plan_sample(mdt_plan* plan, const float* cond_dev, int32_t n_ctx, const 
                     uint64_t seed, uint64_t sample_offset, int64_t B, float cond_scale, int32_t clamp,
                     float* out_dev, uint8_t* tokens_dev, void* stream);
 
+/* Inpainting: replaces QMDiffusion.inpaint -> XDiffusion_x.inpaint -> DiffusionInpainter.forward ->
+ * ADPM2Sampler.inpaint (generative.py:871-914, diffusion.py:744-767, 612-625, 526-549).
+ *   source_dev [B, P, L] fp32   the draft to keep where mask != 0;   mask_dev [B, P, L] uint8
+ *   noise_dev  [1 + n_iters * 2 * num_resamples, B, P, L] fp32 in the reference's draw order (initial state; per iteration: source
+ *              noise, then per resample: step noise [, re-noise]) or NULL => Philox keyed by (seed, sample, draw index)
+ *   sigmas     [n_iters + 1] host fp32 (the schedule; used for the re-noise scale sqrt(sigma_i^2 - sigma_{i+1}^2))
+ * No final clamp (the reference's inpainter has none).  Asynchronous on `stream`. */
+int mdt_plan_inpaint(mdt_plan* plan, const float* cond_dev, int32_t n_ctx, const float* source_dev, const uint8_t* mask_dev,
+                     const float* noise_dev, const mdt_iter_scalars* iters, const float* sigmas, int32_t n_iters,
+                     int32_t num_resamples, uint64_t seed, uint64_t sample_offset, int64_t B, float cond_scale, float* out_dev,
+                     void* stream);
+
 /* One raw denoiser-network evaluation (UNetCFG1d.forward, modules.py:1228-1255) for kernel-level
  * parity tests: x_dev [B,P,L], scalar `time` (= c_noise) shared by the batch, out_dev [B,P,L]. */
 int mdt_plan_unet_forward(mdt_plan* plan, const float* x_dev, float time, const float* cond_dev,

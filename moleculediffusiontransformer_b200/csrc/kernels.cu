@@ -688,7 +688,7 @@ __global__ void step_update_kernel(const StepParams p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const int e = g * 4 + j; const int l = e / P, pp = e - l * P; nz[j] = tile[pp * (L + 1) + l]; }
       } else {
-        const float4 z = philox_normal4(p.seed, p.sample_offset + b, (unsigned)(iter + 1), (unsigned)g);
+        const float4 z = philox_normal4(p.seed, p.sample_offset + b, p.noise_stream >= 0 ? (unsigned)p.noise_stream : (unsigned)(iter + 1), (unsigned)g);
         nz[0] = z.x; nz[1] = z.y; nz[2] = z.z; nz[3] = z.w;
       }
     }
@@ -808,6 +808,51 @@ cudaError_t launch_finalize(const float* x, float* out, unsigned char* tokens, i
                             cudaStream_t s) {
   if (B <= 0) return cudaSuccess;
   finalize_kernel<<<B, 256, (size_t)L * (P + 1) * sizeof(float), s>>>(x, out, tokens, P, L, clamp);
+  return cudaGetLastError();
+}
+
+// ---- inpainting (ADPM2Sampler.inpaint, diffusion.py:526-549) -----------------------------------------------------------
+// mode 0: x = sigma * n                                   (initial state, diffusion.py:535)
+// mode 1: x = mask ? source + sigma * n : x               (merge of the re-noised source, diffusion.py:539-542) + network input
+// mode 2: x = x + sigma * n                               (re-noise between resamples, diffusion.py:545-547)
+// mode 3: out(B,P,L) = mask ? source : x                  (diffusion.py:549)
+// n is injected noise in the reference (B,P,L) layout or Philox(seed, sample, stream, element); x / xin are token-major.
+__global__ void inpaint_kernel(int mode, float* __restrict__ x, float* __restrict__ xin, const float* __restrict__ source,
+                               const unsigned char* __restrict__ mask, const float* __restrict__ noise, float sigma, float c_in,
+                               unsigned long long seed, unsigned long long sample_offset, int stream, int B, int P, int L, int cfg,
+                               float* __restrict__ out) {
+  const int b = blockIdx.x, n = P * L;
+  for (int g = threadIdx.x; g < n / 4; g += blockDim.x) {
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mode != 3 && !noise) z = philox_normal4(seed, sample_offset + b, (unsigned)stream, (unsigned)g);
+    const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = g * 4 + j;                 // token-major element: e = l * P + p
+      const int l = e / P, pp = e - l * P;
+      const size_t bpl = (size_t)b * n + (size_t)pp * L + l;
+      const size_t tm = (size_t)b * n + e;
+      const float nz = (mode != 3 && noise) ? noise[bpl] : zz[j];
+      float v;
+      if (mode == 0) v = sigma * nz;
+      else if (mode == 1) v = mask[bpl] ? source[bpl] + sigma * nz : x[tm];
+      else if (mode == 2) v = x[tm] + sigma * nz;
+      else { out[bpl] = mask[bpl] ? source[bpl] : x[tm]; continue; }
+      x[tm] = v;
+      if (mode == 1) {
+        xin[tm] = c_in * v;
+        if (cfg) xin[(size_t)B * n + tm] = c_in * v;
+      }
+    }
+  }
+}
+
+cudaError_t launch_inpaint(int mode, float* x, float* xin, const float* source, const unsigned char* mask, const float* noise,
+                           float sigma, float c_in, unsigned long long seed, unsigned long long sample_offset, int stream, int B,
+                           int P, int L, int cfg, float* out, cudaStream_t s) {
+  if (B <= 0) return cudaSuccess;
+  if ((P * L) % 4) return cudaErrorInvalidValue;
+  inpaint_kernel<<<B, 256, 0, s>>>(mode, x, xin, source, mask, noise, sigma, c_in, seed, sample_offset, stream, B, P, L, cfg, out);
   return cudaGetLastError();
 }
 

@@ -93,6 +93,7 @@ struct StepParams {
   int cfg;                   // 1 => two branches
   int B, P, L;
   int n_iters;
+  int noise_stream;          // Philox stream id override for the ancestral noise (< 0: iteration + 1)
   float* out;                // final (B,P,L) result written when the last iteration completes (may be null)
   unsigned char* tokens;     // final argmax tokens [B][L] (may be null)
   int clamp;
@@ -131,6 +132,9 @@ cudaError_t launch_step_init(const float* noise0, float* x, float* xin, const It
 cudaError_t launch_step_update(int which, const StepParams& p, cudaStream_t s);
 cudaError_t launch_finalize(const float* x, float* out, unsigned char* tokens, int B, int P, int L, int clamp,
                             cudaStream_t s);
+cudaError_t launch_inpaint(int mode, float* x, float* xin, const float* source, const unsigned char* mask, const float* noise,
+                           float sigma, float c_in, unsigned long long seed, unsigned long long sample_offset, int stream, int B,
+                           int P, int L, int cfg, float* out, cudaStream_t s);
 cudaError_t launch_set_int(int* dst, int v, cudaStream_t s);
 cudaError_t launch_add_int(int* dst, int v, cudaStream_t s);
 // (B,P,L) <-> token-major [B*L][P], with optional duplication into a second half (classifier-free null rows)

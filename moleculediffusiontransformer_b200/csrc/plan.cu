@@ -1213,7 +1213,7 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
       sp.noise = step_noise_dev ? step_noise_dev + (size_t)b0 * per : nullptr;
       sp.noise_iter_stride = (long long)B * (long long)per;
       sp.seed = seed; sp.sample_offset = sample_offset + (uint64_t)b0; sp.cond_scale = cond_scale; sp.cfg = cfg ? 1 : 0;
-      sp.B = Bc; sp.P = P; sp.L = L; sp.n_iters = n_iters; sp.out = nullptr; sp.tokens = nullptr; sp.clamp = clamp;
+      sp.B = Bc; sp.P = P; sp.L = L; sp.n_iters = n_iters; sp.noise_stream = -1; sp.out = nullptr; sp.tokens = nullptr; sp.clamp = clamp;
       if (pl->use_graph && !pl->taps_on) {
         // one captured iteration, replayed n_iters times; all per-iteration data is device resident
         std::vector<long long> key = {Bc, n_ctx, cfg ? 1 : 0, (long long)(uintptr_t)sp.noise, sp.noise_iter_stride,
@@ -1247,6 +1247,72 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
       CK(launch_finalize(pl->x, out_dev ? out_dev + (size_t)b0 * per : nullptr,
                          tokens_dev ? tokens_dev + (size_t)b0 * L : nullptr, Bc, P, L, clamp, s));
       pl->launches++;
+    }
+  } catch (const MdtError& e) {
+    snprintf(g_err, sizeof(g_err), "%s", e.msg.c_str());
+    return e.code;
+  }
+  return 0;
+}
+
+int mdt_plan_inpaint(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const float* source_dev, const uint8_t* mask_dev,
+                     const float* noise_dev, const mdt_iter_scalars* iters, const float* sigmas, int32_t n_iters,
+                     int32_t num_resamples, uint64_t seed, uint64_t sample_offset, int64_t B, float cond_scale, float* out_dev,
+                     void* stream) {
+  if (!pl || !cond_dev || !source_dev || !mask_dev || !iters || !sigmas || !out_dev) return fail(MDT_ERR_INVALID, "null argument");
+  if (B < 0 || n_iters < 1 || num_resamples < 1) return fail(MDT_ERR_INVALID, "bad batch / timesteps / num_resamples");
+  if (2 * n_iters > pl->max_calls) return fail(MDT_ERR_INVALID, "timesteps %d exceeds the plan's max_timesteps %d", n_iters + 1, pl->max_calls / 2 + 1);
+  if (check_ctx(pl, n_ctx)) return MDT_ERR_INVALID;
+  if (pl->cfg.in_channels != pl->cfg.out_channels) return fail(MDT_ERR_INVALID, "sampler needs in_channels == out_channels");
+  if (B == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  try {
+    CK(cudaSetDevice(pl->device));
+    const bool cfg = cond_scale != 1.0f;
+    const int P = pl->P, L = pl->L0, R = num_resamples;
+    const size_t per = (size_t)P * L;
+    const long long draws_per_iter = 2LL * R;              // source noise + R step noises + (R - 1) re-noises
+    CK(cudaStreamSynchronize(s));
+    memcpy(pl->h_iters, iters, sizeof(IterScalars) * n_iters);
+    for (int i = 0; i < n_iters; ++i) { pl->h_tcalls[2 * i] = iters[i].c_noise_a; pl->h_tcalls[2 * i + 1] = iters[i].c_noise_b; }
+    CK(cudaMemcpyAsync(pl->d_iters, pl->h_iters, sizeof(IterScalars) * n_iters, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(pl->t_calls, pl->h_tcalls, sizeof(float) * 2 * n_iters, cudaMemcpyHostToDevice, s));
+    run_time_tables(*pl, 2 * n_iters, s);
+    for (int64_t b0 = 0; b0 < B; b0 += pl->Bmax) {
+      const int Bc = (int)std::min<int64_t>(pl->Bmax, B - b0);
+      const int Beff = cfg ? 2 * Bc : Bc;
+      run_context(*pl, cond_dev + (size_t)b0 * n_ctx, Bc, n_ctx, cfg, s);
+      const float* src = source_dev + (size_t)b0 * per;
+      const uint8_t* msk = mask_dev + (size_t)b0 * per;
+      // draw d of the reference's RNG sequence lives at noise_dev[d][B][P][L]
+      auto nz = [&](long long d) -> const float* { return noise_dev ? noise_dev + ((size_t)d * B + (size_t)b0) * per : nullptr; };
+      const uint64_t off = sample_offset + (uint64_t)b0;
+      CK(launch_inpaint(0, pl->x, pl->xin, src, msk, nz(0), iters[0].sigma, 0.f, seed, off, 0, Bc, P, L, cfg, nullptr, s));
+      StepParams sp{};
+      sp.iters = pl->d_iters; sp.call_idx = pl->d_call; sp.net = pl->net_out; sp.x = pl->x; sp.xmid = pl->xmid; sp.xin = pl->xin;
+      sp.noise_iter_stride = 0; sp.seed = seed; sp.sample_offset = off; sp.cond_scale = cond_scale; sp.cfg = cfg ? 1 : 0;
+      sp.B = Bc; sp.P = P; sp.L = L; sp.n_iters = n_iters; sp.out = nullptr; sp.tokens = nullptr; sp.clamp = 0;
+      for (int i = 0; i < n_iters; ++i) {
+        long long d = 1 + (long long)i * draws_per_iter;
+        const long long d_src = d++;
+        for (int r = 0; r < R; ++r) {
+          CK(launch_inpaint(1, pl->x, pl->xin, src, msk, nz(d_src), iters[i].sigma, iters[i].c_in_a, seed, off, (int)d_src, Bc, P, L,
+                            cfg, nullptr, s));
+          CK(launch_set_int(pl->d_call, 2 * i, s));
+          const long long d_step = d++;
+          sp.noise = nz(d_step); sp.noise_stream = (int)d_step;
+          run_iteration(*pl, sp, Beff, Bc, n_ctx, s);
+          pl->launches += 2;
+          if (r < R - 1) {
+            const long long d_re = d++;
+            const float sg = (float)sqrt((double)(sigmas[i] * sigmas[i] - sigmas[i + 1] * sigmas[i + 1]));
+            CK(launch_inpaint(2, pl->x, pl->xin, src, msk, nz(d_re), sg, 0.f, seed, off, (int)d_re, Bc, P, L, cfg, nullptr, s));
+            pl->launches++;
+          }
+        }
+      }
+      CK(launch_inpaint(3, pl->x, pl->xin, src, msk, nullptr, 0.f, 0.f, seed, off, 0, Bc, P, L, cfg, out_dev + (size_t)b0 * per, s));
+      pl->launches += 2;
     }
   } catch (const MdtError& e) {
     snprintf(g_err, sizeof(g_err), "%s", e.msg.c_str());
@@ -1298,7 +1364,7 @@ int mdt_op_step_update(int which, const float* net_dev, float* x_dev, float* xmi
   StepParams sp{};
   sp.iters = d_it; sp.call_idx = d_call; sp.net = net_dev; sp.x = x_dev; sp.xmid = xmid_dev; sp.xin = xin_dev;
   sp.noise = noise_dev; sp.noise_iter_stride = 0; sp.seed = 0; sp.sample_offset = 0; sp.cond_scale = cond_scale; sp.cfg = cfg;
-  sp.B = (int)B; sp.P = P; sp.L = L; sp.n_iters = 2; sp.clamp = 0;
+  sp.B = (int)B; sp.P = P; sp.L = L; sp.n_iters = 2; sp.noise_stream = -1; sp.clamp = 0;
   cudaError_t e = launch_step_update(which, sp, s);
   if (e != cudaSuccess) return fail(MDT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return 0;

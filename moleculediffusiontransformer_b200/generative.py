@@ -145,8 +145,27 @@ class _QMBase(nn.Module):
             noise=noise, embedding=None, embedding_scale=cond_scale, sequences=sequences.to(device),
             step_noise=step_noise, seed=seed, precision=precision, return_tokens=return_tokens)
 
-    def inpaint(self, *a, **k):
-        raise NotImplementedError("inpainting (generative.py:871-914) is a 'next' row of the scope table")
+    def inpaint(self, sequences, device, cond_scale=7.5, timesteps=100, num_resamples=1, inpaint=None, in_paint_mask=None, *,
+                noise=None, seed=None, precision=None):
+        """Conditional inpainting (generative.py:871-914 / 182-225): positions where ``in_paint_mask`` is True keep ``inpaint``.
+
+        Positional arguments are the reference's.  ``noise`` optionally injects every RNG draw of ADPM2Sampler.inpaint
+        (diffusion.py:526-549) as a ``(1 + (timesteps-1)*2*num_resamples, B, P, L)`` tensor in draw order; otherwise the draws
+        come from the in-kernel Philox stream (seed taken from torch's CPU generator unless given)."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("moleculediffusiontransformer_b200 runs on sm_100a CUDA devices only "
+                               f"(got device={device}); there is no CPU path")
+        if inpaint is None or in_paint_mask is None:
+            raise ValueError("inpaint and in_paint_mask are required")
+        if sequences.shape[1] > self.unet.fixed_embedding.max_length:
+            raise AssertionError("Input sequence length must be <= max_length")  # modules.py:1194-1195
+        if seed is None and noise is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        plan = self._plan_for(device, precision, batch=sequences.shape[0])
+        return plan.inpaint(sequences.to(device), inpaint, in_paint_mask, num_steps=timesteps, num_resamples=num_resamples,
+                            sigma_schedule=KarrasSchedule(sigma_min=0.001, sigma_max=9.0, rho=3.0), sampler=ADPM2Sampler(rho=1),
+                            cond_scale=float(cond_scale), noise=noise, seed=seed)
 
 
 class QMDiffusion(_QMBase):

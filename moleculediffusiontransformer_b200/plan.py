@@ -144,6 +144,35 @@ class SamplerPlan:
                     t.record_stream(torch.cuda.current_stream(self.device))
         return (out, tokens) if return_tokens else out
 
+    def inpaint(self, sequences, source, mask, *, num_steps: int, num_resamples: int, sigma_schedule, sampler,
+                cond_scale: float, noise=None, seed: Optional[int] = None, sample_offset: int = 0):
+        """ADPM2Sampler.inpaint (diffusion.py:526-549) on the device: keep `source` where `mask` is True."""
+        if num_steps > self.max_timesteps:
+            raise ValueError(f"timesteps={num_steps} exceeds this plan's max_timesteps={self.max_timesteps}")
+        b, n_ctx = sequences.shape
+        P, L = self.pred_dim, self.max_length
+        sigmas = sigma_schedule(num_steps, "cpu").detach().to(torch.float32).contiguous()
+        table = np.ascontiguousarray(build_iter_scalars(sigmas, num_steps, sampler, self.sigma_data))
+        draws = 1 + (num_steps - 1) * 2 * num_resamples
+        if tuple(source.shape) != (b, P, L) or tuple(mask.shape) != (b, P, L):
+            raise ValueError(f"inpaint and in_paint_mask must have shape {(b, P, L)}")
+        with torch.cuda.device(self.device):
+            cond, src = self._dev32(sequences), self._dev32(source)
+            msk = mask.detach().to(self.device).to(torch.uint8).contiguous()
+            nz = self._dev32(noise) if noise is not None else None
+            if nz is not None and tuple(nz.shape) != (draws, b, P, L):
+                raise ValueError(f"noise must have shape {(draws, b, P, L)}")
+            out = torch.empty((b, P, L), dtype=torch.float32, device=self.device)
+            sig = sigmas.numpy()
+            _capi.check(self.lib.mdt_plan_inpaint(
+                self.handle, cond.data_ptr(), n_ctx, src.data_ptr(), msk.data_ptr(), nz.data_ptr() if nz is not None else None,
+                table.ctypes.data, sig.ctypes.data, table.shape[0], int(num_resamples), int(seed or 0), int(sample_offset), b,
+                float(cond_scale), out.data_ptr(), self._stream()))
+            for t in (cond, src, msk, nz):
+                if t is not None:
+                    t.record_stream(torch.cuda.current_stream(self.device))
+        return out
+
     def unet_forward(self, x, time: float, sequences, cond_scale: float = 1.0, taps=None):
         """One UNetCFG1d evaluation (modules.py:1228-1255) -- kernel-level parity entry point."""
         b, n_ctx = sequences.shape

@@ -39,3 +39,24 @@ def make_inputs(name: str):
     noise0 = torch.randn(b, p, l, generator=g)
     step_noise = torch.randn(steps - 1, b, p, l, generator=g)
     return seq, noise0, step_noise
+
+
+# inpainting cases: name -> (ctor kwargs, model seed, data seed, batch, ctx_len, cond_scale, timesteps, num_resamples, keep_positions)
+INPAINT_CASES = {
+    "inpaint_inv64_r1": (INV64, 0, 41, 3, 12, 2.0, 6, 1, 20),
+    "inpaint_inv64_r2": (INV64, 0, 42, 2, 12, 7.5, 5, 2, 33),
+}
+
+
+def make_inpaint_inputs(name: str):
+    kw, mseed, dseed, b, n, cs, steps, resamples, keep = INPAINT_CASES[name]
+    g = torch.Generator().manual_seed(dseed)
+    seq = torch.rand(b, n, generator=g) * 2 - 1
+    p, l = kw["pred_dim"], kw["max_length"]
+    # a one-hot-like draft in [-1, 1] (what inpaint_from_draft_and_conditioning builds, generative.py:1574-1660)
+    tok = torch.randint(0, p, (b, l), generator=g)
+    source = torch.nn.functional.one_hot(tok, p).permute(0, 2, 1).float() * 2 - 1
+    mask = torch.zeros(b, p, l, dtype=torch.bool)
+    mask[:, :, :keep] = True                      # keep the first `keep` positions (sequential_mask, diffusion.py:628-632)
+    draws = torch.randn(1 + (steps - 1) * 2 * resamples, b, p, l, generator=g)
+    return seq, source, mask, draws

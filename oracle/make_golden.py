@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import reference_loader as rl  # noqa: E402
-from oracle.cases import CASES, make_inputs  # noqa: E402
+from oracle.cases import CASES, INPAINT_CASES, make_inpaint_inputs, make_inputs  # noqa: E402
 
 
 def main(names=None):
@@ -48,5 +48,19 @@ def main(names=None):
         print(f"{name}: out.sum={out.double().sum():.6f} net.sum={net.double().sum():.6f} params={pcount}")
 
 
+def main_inpaint():
+    for name, (kw, mseed, dseed, b, n, cs, steps, resamples, keep) in INPAINT_CASES.items():
+        m = rl.build_model("inverse", seed=mseed, **kw)
+        seq, source, mask, draws = make_inpaint_inputs(name)
+        with rl.injected_noise(torch.zeros(0), list(draws)) as st:
+            out = m.inpaint(seq, "cpu", cond_scale=cs, timesteps=steps, num_resamples=resamples, inpaint=source, in_paint_mask=mask)
+        assert st["i"] == draws.shape[0], (st["i"], draws.shape[0])
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"{name}.npz"), out=out.numpy())
+        print(f"{name}: out.sum={out.double().sum():.6f} draws={st['i']}")
+
+
 if __name__ == "__main__":
-    main(sys.argv[1:] or None)
+    if sys.argv[1:] == ["inpaint"]:
+        main_inpaint()
+    else:
+        main(sys.argv[1:] or None)

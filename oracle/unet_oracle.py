@@ -243,6 +243,40 @@ def adpm2_sample(fn: Callable, noise: Tensor, sigmas: Tensor, num_steps: int, st
     return x
 
 
+def adpm2_inpaint(fn: Callable, source: Tensor, mask: Tensor, sigmas: Tensor, num_steps: int, num_resamples: int, draws,
+                  rho: float = 1.0) -> Tensor:
+    """ADPM2Sampler.inpaint (diffusion.py:526-549); ``draws`` replays every randn_like in call order."""
+    it = iter(draws)
+    x = sigmas[0] * next(it)
+    for i in range(num_steps - 1):
+        source_noisy = source + sigmas[i] * next(it)
+        for r in range(num_resamples):
+            x = source_noisy * mask + x * ~mask
+            sigma, sigma_next = sigmas[i], sigmas[i + 1]
+            sigma_up = math.sqrt(sigma_next ** 2 * (sigma ** 2 - sigma_next ** 2) / sigma ** 2)
+            sigma_down = math.sqrt(sigma_next ** 2 - sigma_up ** 2)
+            sigma_mid = ((sigma ** (1 / rho) + sigma_down ** (1 / rho)) / 2) ** rho
+            d = (x - fn(x, sigma)) / sigma
+            x_mid = x + d * (sigma_mid - sigma)
+            d_mid = (x_mid - fn(x_mid, sigma_mid)) / sigma_mid
+            x = x + d_mid * (sigma_down - sigma)
+            x = x + next(it) * sigma_up
+            if r < num_resamples - 1:
+                s = math.sqrt(sigmas[i] ** 2 - sigmas[i + 1] ** 2)
+                x = x + s * next(it)
+    return source * mask + x * ~mask
+
+
+@torch.no_grad()
+def inpaint(sd: SD, cfg: dict, sequences: Tensor, source: Tensor, mask: Tensor, draws, cond_scale: float, timesteps: int,
+            num_resamples: int = 1) -> Tensor:
+    """QMDiffusion.inpaint (generative.py:871-914) -> DiffusionInpainter.forward (diffusion.py:612-625), injected noise."""
+    emb = encode_conditioning(sd, sequences)
+    sigmas = karras_sigmas(timesteps)
+    fn = lambda x, sigma: denoise(sd, cfg, x, sigma, emb, cond_scale)
+    return adpm2_inpaint(fn, source, mask, sigmas, timesteps, num_resamples, draws)
+
+
 @torch.no_grad()
 def sample(sd: SD, cfg: dict, sequences: Tensor, noise0: Tensor, step_noise, cond_scale: float, timesteps: int,
            clamp: bool = False, pos_emb_fourier: bool = True, pos_emb_fourier_add: bool = False) -> Tensor:

@@ -5,7 +5,7 @@ import torch
 
 from conftest import golden
 from oracle import unet_oracle as orc
-from oracle.cases import CASES, INV64, make_inputs
+from oracle.cases import CASES, INPAINT_CASES, INV64, make_inpaint_inputs, make_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -151,6 +151,31 @@ def test_launcher_single_process_matches_direct_call(model_cache):
     tok = sharded_sample(model_runner(m, "cuda:0", 5.0, 6, seed=11, precision="tf32"), seq)
     out, want = m.sample(seq, "cuda:0", cond_scale=5.0, timesteps=6, seed=11, precision="tf32", return_tokens=True)
     assert tok.dtype == torch.uint8 and tok.shape == (5, 64) and torch.equal(tok, want)
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("tf32", 2e-3)])
+@pytest.mark.parametrize("name", list(INPAINT_CASES))
+def test_inpaint_vs_reference_fixture(name, prec, tol, model_cache):
+    """QMDiffusion.inpaint with the reference's injected RNG draws (generative.py:871-914, diffusion.py:526-549)."""
+    kw, mseed, dseed, b, n, cs, steps, resamples, keep = INPAINT_CASES[name]
+    m = model_cache("inverse", kw, mseed)
+    seq, source, mask, draws = make_inpaint_inputs(name)
+    got = m.inpaint(seq, "cuda:0", cond_scale=cs, timesteps=steps, num_resamples=resamples, inpaint=source, in_paint_mask=mask,
+                    noise=draws, precision=prec).cpu()
+    ref = torch.from_numpy(golden(name)["out"])
+    assert got.shape == ref.shape
+    assert torch.equal(got[:, :, :keep], source[:, :, :keep])
+    assert orc.rel_l2(got[:, :, keep:], ref[:, :, keep:]) < tol
+
+
+def test_inpaint_philox_is_deterministic_and_seeded(model_cache):
+    m = model_cache("inverse", INV64, 0)
+    seq, source, mask, _ = make_inpaint_inputs("inpaint_inv64_r2")
+    kw = dict(cond_scale=3.0, timesteps=5, num_resamples=2, inpaint=source, in_paint_mask=mask, precision="tf32")
+    a = m.inpaint(seq, "cuda:0", seed=4, **kw)
+    b = m.inpaint(seq, "cuda:0", seed=4, **kw)
+    c = m.inpaint(seq, "cuda:0", seed=5, **kw)
+    assert torch.equal(a, b) and not torch.equal(a, c) and torch.isfinite(a).all()
 
 
 def test_reference_error_behaviour(model_cache):

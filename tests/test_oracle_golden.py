@@ -5,7 +5,7 @@ import torch
 
 from conftest import golden
 from oracle import unet_oracle as orc
-from oracle.cases import CASES, make_inputs
+from oracle.cases import CASES, INPAINT_CASES, make_inpaint_inputs, make_inputs
 
 FAST = ["inv64_cs1", "inv64_short_ctx_clamp", "fwd64_cs2", "paper_cs2"]
 
@@ -63,3 +63,16 @@ def test_survey_self_check_values():
     assert toks[0, :16].tolist() == [8, 11, 1, 11, 9, 13, 14, 5, 1, 9, 9, 3, 11, 0, 11, 3]
     g2 = golden("inv64_cs7p5")["out"]
     assert float(g2.astype(np.float64).sum()) == pytest.approx(289.317932, abs=4e-4)
+
+
+@pytest.mark.parametrize("name", list(INPAINT_CASES))
+def test_inpaint_matches_reference(name, model_cache):
+    """Oracle restatement of ADPM2Sampler.inpaint against fixtures produced by the reference's QMDiffusion.inpaint."""
+    kw, mseed, dseed, b, n, cs, steps, resamples, keep = INPAINT_CASES[name]
+    m = model_cache("inverse", kw, mseed)
+    sd, cfg = _sd_cfg(m)
+    seq, source, mask, draws = make_inpaint_inputs(name)
+    out = orc.inpaint(sd, cfg, seq, source, mask, list(draws), cs, steps, resamples)
+    ref = torch.from_numpy(golden(name)["out"])
+    assert orc.rel_l2(out, ref) < 1e-5
+    assert torch.equal(out[:, :, :keep], source[:, :, :keep])          # kept region is the draft, bit for bit
