@@ -178,6 +178,21 @@ def test_inpaint_philox_is_deterministic_and_seeded(model_cache):
     assert torch.equal(a, b) and not torch.equal(a, c) and torch.isfinite(a).all()
 
 
+def test_closed_loop_screening_stays_on_device(model_cache):
+    """inverse tokens feed the forward plan directly; equals the two calls made separately."""
+    from moleculediffusiontransformer_b200.screening import generate_and_score, tokens_to_forward_conditioning
+    from oracle.cases import FWD64
+
+    inv, fwd = model_cache("inverse", INV64, 0), model_cache("forward", FWD64, 0)
+    g = torch.Generator().manual_seed(3)
+    seq = torch.rand(6, 12, generator=g) * 2 - 1
+    tokens, pred = generate_and_score(inv, fwd, seq, "cuda:0", cond_scale=5.0, timesteps=6, seed=21, precision="tf32")
+    assert tokens.is_cuda and pred.is_cuda and tokens.shape == (6, 64) and pred.shape == (6, 1, 64)
+    _, tok2 = inv.sample(seq, "cuda:0", cond_scale=5.0, timesteps=6, seed=21, precision="tf32", return_tokens=True)
+    pred2 = fwd.sample(tokens_to_forward_conditioning(tok2, 64, 21.0), "cuda:0", cond_scale=1.0, timesteps=6, seed=22, precision="tf32")
+    assert torch.equal(tokens, tok2) and torch.equal(pred, pred2) and torch.isfinite(pred).all()
+
+
 def test_reference_error_behaviour(model_cache):
     m = model_cache("inverse", INV64, 0)
     with pytest.raises(AssertionError):                                  # modules.py:1194-1195

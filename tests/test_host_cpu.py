@@ -149,3 +149,16 @@ def test_sharded_gather_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=120) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "OK" in outs[0][0]
+
+
+def test_tokens_to_forward_conditioning_matches_text_round_trip():
+    """Compaction of padding + normalisation == decode to text, re-tokenise, divide, pad (generative.py:682-685, 1069-1078)."""
+    from moleculediffusiontransformer_b200.screening import tokens_to_forward_conditioning
+
+    toks = torch.tensor([[3, 0, 5, 5, 0, 0, 1, 2], [0, 0, 0, 0, 0, 0, 0, 0], [7, 6, 5, 4, 3, 2, 1, 9]], dtype=torch.uint8)
+    got = tokens_to_forward_conditioning(toks, 6, 21.0)
+    want = torch.zeros(3, 6)
+    for i, row in enumerate(toks.tolist()):
+        ids = [t for t in row if t != 0][:6]
+        want[i, : len(ids)] = torch.tensor(ids, dtype=torch.float32) / 21.0
+    assert torch.equal(got, want)
