@@ -11,6 +11,13 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu via gpurun)")
     config.addinivalue_line("markers", "slow: larger CPU case")
+    # the C-ABI library is a build artefact (git-ignored): compile it for sm_100a if this checkout has not done so yet
+    lib = os.path.join(ROOT, "moleculediffusiontransformer_b200", "libmdt_b200.so")
+    if not os.path.exists(lib):
+        import subprocess
+
+        subprocess.run(["make", "-C", os.path.join(ROOT, "moleculediffusiontransformer_b200", "csrc"), "-j4"], check=True,
+                       stdout=subprocess.DEVNULL)
 
 
 @pytest.fixture(scope="session")
