@@ -688,7 +688,8 @@ __global__ void step_update_kernel(const StepParams p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const int e = g * 4 + j; const int l = e / P, pp = e - l * P; nz[j] = tile[pp * (L + 1) + l]; }
       } else {
-        const float4 z = philox_normal4(p.seed, p.sample_offset + b, p.noise_stream >= 0 ? (unsigned)p.noise_stream : (unsigned)(iter + 1), (unsigned)g);
+        const unsigned long long sd = p.rng ? p.rng[0] : p.seed, so = p.rng ? p.rng[1] : p.sample_offset;
+        const float4 z = philox_normal4(sd, so + b, p.noise_stream >= 0 ? (unsigned)p.noise_stream : (unsigned)(iter + 1), (unsigned)g);
         nz[0] = z.x; nz[1] = z.y; nz[2] = z.z; nz[3] = z.w;
       }
     }
@@ -722,6 +723,11 @@ cudaError_t launch_step_update(int which, const StepParams& p, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+__global__ void set_u64x2_kernel(unsigned long long* dst, unsigned long long a, unsigned long long b) { dst[0] = a; dst[1] = b; }
+cudaError_t launch_set_u64x2(unsigned long long* dst, unsigned long long a, unsigned long long b, cudaStream_t s) {
+  set_u64x2_kernel<<<1, 1, 0, s>>>(dst, a, b);
+  return cudaGetLastError();
+}
 __global__ void set_int_kernel(int* dst, int v) { *dst = v; }
 __global__ void add_int_kernel(int* dst, int v) { *dst += v; }
 cudaError_t launch_set_int(int* dst, int v, cudaStream_t s) { set_int_kernel<<<1, 1, 0, s>>>(dst, v); return cudaGetLastError(); }

@@ -89,6 +89,7 @@ struct StepParams {
   const float* noise;        // injected ancestral noise (B,P,L) for this iteration, or null => Philox
   long long noise_iter_stride;  // floats between iterations in the injected noise tensor
   unsigned long long seed, sample_offset;
+  const unsigned long long* rng;  // optional device pair {seed, sample_offset} overriding the two fields above (graph replays)
   float cond_scale;
   int cfg;                   // 1 => two branches
   int B, P, L;
@@ -135,6 +136,7 @@ cudaError_t launch_finalize(const float* x, float* out, unsigned char* tokens, i
 cudaError_t launch_inpaint(int mode, float* x, float* xin, const float* source, const unsigned char* mask, const float* noise,
                            float sigma, float c_in, unsigned long long seed, unsigned long long sample_offset, int stream, int B,
                            int P, int L, int cfg, float* out, cudaStream_t s);
+cudaError_t launch_set_u64x2(unsigned long long* dst, unsigned long long a, unsigned long long b, cudaStream_t s);
 cudaError_t launch_set_int(int* dst, int v, cudaStream_t s);
 cudaError_t launch_add_int(int* dst, int v, cudaStream_t s);
 // (B,P,L) <-> token-major [B*L][P], with optional duplication into a second half (classifier-free null rows)

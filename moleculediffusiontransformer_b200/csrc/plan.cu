@@ -140,6 +140,7 @@ struct mdt_plan {
   IterScalars* h_iters = nullptr;  // pinned
   float* h_tcalls = nullptr;       // pinned
   int* d_call = nullptr;
+  unsigned long long* d_rng = nullptr;   // {seed, first sample index} of the running chunk, read by the captured step kernels
   int n_ctx_cur = 0;
   // graph cache: key (Bc, n_ctx, cfg, has_step_noise)
   struct GraphEntry { cudaGraphExec_t exec; };
@@ -1080,6 +1081,7 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
     CK(cudaMallocHost((void**)&pl->h_tcalls, sizeof(float) * (pl->max_calls + 2)));
     CK(cudaMalloc((void**)&pl->d_call, sizeof(int)));
     CK(cudaMemset(pl->d_call, 0, sizeof(int)));
+    CK(cudaMalloc((void**)&pl->d_rng, 2 * sizeof(unsigned long long)));
     Builder b(*pl);
     b.build();
     pl->tensors.clear();  // host pointers are not retained past creation
@@ -1104,6 +1106,7 @@ void mdt_plan_destroy(mdt_plan* pl) {
   if (pl->h_iters) cudaFreeHost(pl->h_iters);
   if (pl->h_tcalls) cudaFreeHost(pl->h_tcalls);
   if (pl->d_call) cudaFree(pl->d_call);
+  if (pl->d_rng) cudaFree(pl->d_rng);
   cudaGetLastError();
   delete pl;
 }
@@ -1213,12 +1216,13 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
       sp.noise = step_noise_dev ? step_noise_dev + (size_t)b0 * per : nullptr;
       sp.noise_iter_stride = (long long)B * (long long)per;
       sp.seed = seed; sp.sample_offset = sample_offset + (uint64_t)b0; sp.cond_scale = cond_scale; sp.cfg = cfg ? 1 : 0;
+      sp.rng = pl->d_rng;   // seed / offset live in device memory so that one captured graph serves every seed and shard
+      CK(launch_set_u64x2(pl->d_rng, seed, sample_offset + (uint64_t)b0, s));
       sp.B = Bc; sp.P = P; sp.L = L; sp.n_iters = n_iters; sp.noise_stream = -1; sp.out = nullptr; sp.tokens = nullptr; sp.clamp = clamp;
       if (pl->use_graph && !pl->taps_on) {
         // one captured iteration, replayed n_iters times; all per-iteration data is device resident
         std::vector<long long> key = {Bc, n_ctx, cfg ? 1 : 0, (long long)(uintptr_t)sp.noise, sp.noise_iter_stride,
-                                      (long long)seed, (long long)sp.sample_offset, (long long)n_iters,
-                                      (long long)(cond_scale * 65536.0)};
+                                      (long long)n_iters, (long long)(cond_scale * 65536.0)};
         auto it = pl->graphs.find(key);
         if (it == pl->graphs.end()) {
           if (pl->graphs.size() > 16) { for (auto& kv : pl->graphs) cudaGraphExecDestroy(kv.second.exec); pl->graphs.clear(); }
