@@ -66,7 +66,8 @@ class _QMBase(nn.Module):
         self._plans = {}
 
     # ------------------------------------------------------------------ plan management
-    def _plan_for(self, device: torch.device, precision: Optional[str] = None, batch: Optional[int] = None):
+    def _plan_for(self, device: torch.device, precision: Optional[str] = None, batch: Optional[int] = None,
+                  timesteps: int = 0):
         """One cached plan per (device, precision).  The workspace is sized for a power-of-two chunk that covers `batch`
         (capped at MDT_MAX_BATCH, default 4096); a larger request rebuilds the plan, a smaller one reuses it."""
         from .plan import SamplerPlan, default_max_batch, default_precision
@@ -77,10 +78,11 @@ class _QMBase(nn.Module):
         version = sum(p._version for p in self.parameters())
         cap = default_max_batch()
         want = cap if batch is None else min(cap, max(8, 1 << (max(int(batch), 1) - 1).bit_length()))
-        if plan is None or plan.weights_version != version or plan.max_batch < want:
+        steps = max(256, 1 << (max(int(timesteps), 2) - 1).bit_length())      # FiLM tables are sized per denoiser call
+        if plan is None or plan.weights_version != version or plan.max_batch < want or plan.max_timesteps < timesteps:
             if plan is not None:
                 plan.close()
-            plan = SamplerPlan(self, device, precision=precision, max_batch=want)
+            plan = SamplerPlan(self, device, precision=precision, max_batch=want, max_timesteps=steps)
             plan.weights_version = version
             self._plans[key] = plan
         return plan
@@ -108,7 +110,7 @@ class _QMBase(nn.Module):
             raise NotImplementedError(
                 "the accelerated path encodes the conditioning on the device; call model.sample(sequences, ...)")
         device = noise.device if noise is not None else sequences.device
-        plan = self._plan_for(torch.device(device), precision, batch=sequences.shape[0])
+        plan = self._plan_for(torch.device(device), precision, batch=sequences.shape[0], timesteps=num_steps)
         return plan.sample(sequences, noise0=noise, step_noise=step_noise, num_steps=num_steps,
                            sigma_schedule=sigma_schedule, sampler=sampler, clamp=clamp,
                            cond_scale=float(embedding_scale), seed=seed, return_tokens=return_tokens)
@@ -162,7 +164,7 @@ class _QMBase(nn.Module):
             raise AssertionError("Input sequence length must be <= max_length")  # modules.py:1194-1195
         if seed is None and noise is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        plan = self._plan_for(device, precision, batch=sequences.shape[0])
+        plan = self._plan_for(device, precision, batch=sequences.shape[0], timesteps=timesteps)
         return plan.inpaint(sequences.to(device), inpaint, in_paint_mask, num_steps=timesteps, num_resamples=num_resamples,
                             sigma_schedule=KarrasSchedule(sigma_min=0.001, sigma_max=9.0, rho=3.0), sampler=ADPM2Sampler(rho=1),
                             cond_scale=float(cond_scale), noise=noise, seed=seed)

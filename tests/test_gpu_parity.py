@@ -201,6 +201,10 @@ def test_reference_error_behaviour(model_cache):
         m.sample(torch.zeros(2, 12), "cuda:0", cond_scale=1.0, timesteps=4, noise=torch.zeros(2, 16, 32))
     out = m.sample(torch.zeros(0, 12), "cuda:0", cond_scale=1.0, timesteps=4)   # empty batch
     assert out.shape == (0, 16, 64)
+    long_run = m.sample(torch.zeros(1, 12), "cuda:0", cond_scale=1.0, timesteps=300, seed=1)   # > default table size: plan is rebuilt
+    assert torch.isfinite(long_run).all()
+    with pytest.raises(Exception):
+        m.sample(torch.zeros(1, 12), "cuda:0", cond_scale=1.0, timesteps=1)     # the reference divides by num_steps - 1 == 0
 
 
 @pytest.mark.parametrize("prec", ["tf32"])
