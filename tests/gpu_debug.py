@@ -1,6 +1,6 @@
 """First-contact GPU diagnostics: per-kernel and per-stage errors against the CPU oracle.
 
-    python tools/gpu_debug.py [fp32|tf32|bf16] [case]
+    python tests/gpu_debug.py [fp32|tf32|bf16] [case]        (test infrastructure: it compares against oracle/)
 Prints one line per stage tap so a single gpurun call localises a wrong kernel.
 """
 import os

@@ -7,7 +7,10 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import moleculediffusiontransformer_b200 as mdt
-from oracle.cases import INV64, FWD64, WIDE
+INV64 = dict(max_length=64, pred_dim=16, channels=64, unet_type="cfg", context_embedding_max_length=12,
+             pos_emb_fourier=True, pos_emb_fourier_add=False, text_embed_dim=64, embed_dim_position=64)
+FWD64 = dict(INV64, pred_dim=1, context_embedding_max_length=64)
+WIDE = dict(INV64, max_length=128, pred_dim=32, channels=128)
 
 name = sys.argv[1]
 prec = sys.argv[2] if len(sys.argv) > 2 else "tf32"

@@ -19,7 +19,10 @@ sys.path.insert(0, ROOT)
 import moleculediffusiontransformer_b200 as mdt  # noqa: E402
 from moleculediffusiontransformer_b200 import ADPM2Sampler, KarrasSchedule  # noqa: E402
 from moleculediffusiontransformer_b200.launcher import gather_rows, shard_bounds  # noqa: E402
-from oracle.cases import INV64  # noqa: E402  (constructor kwargs of the README model only)
+
+# README model (BASELINE.json configs[0..1])
+INV64 = dict(max_length=64, pred_dim=16, channels=64, unet_type="cfg", context_embedding_max_length=12,
+             pos_emb_fourier=True, pos_emb_fourier_add=False, text_embed_dim=64, embed_dim_position=64)
 
 
 def main():
