@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
       const uint32_t tx = (uint32_t)(A_ABYTES + b_bytes);
       int c = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int mt = t / p.heads, h = t - mt * p.heads;
+        const int te = p.rev ? total_tiles - 1 - t : t;
+        const int mt = te / p.heads, h = te - mt * p.heads;
         for (int kc = 0; kc < p.kchunks; ++kc, ++c) {
           const int stage = c % A_STAGES;
           const uint32_t phase = (uint32_t)(c / A_STAGES) & 1u;
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
     bool pf_primed = false;
     // cp.async copy of the K / V rows of (tile tt, sample ss) for this tile's head into scratch buffer `bufi`
     auto issue_kv = [&](int tt, int ss, int bufi) {
+      if (p.rev) tt = total_tiles - 1 - tt;
       const int mtt = tt / p.heads, hh = tt - mtt * p.heads;
       const int b = (mtt * A_TM + ss * L) / L;
       const bool nul = p.kn && b >= p.n_cond;
@@ -148,7 +150,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
     };
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int mt = t / p.heads, h = t - mt * p.heads;
+      const int te = p.rev ? total_tiles - 1 - t : t;
+      const int mt = te / p.heads, h = te - mt * p.heads;
       const int m0 = mt * A_TM;
       const int buf = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -200,8 +203,9 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
           // fp32-storage K/V cache: the copy for this item was issued one item ago with cp.async; issue the next one now
           if (!pf_primed) { issue_kv(t, s, pf_buf); pf_primed = true; }
           int nt = t, ns = s + s_step;
-          if (ns >= s_end || nt / p.heads * A_TM + ns * L >= p.M) { nt = t + gridDim.x; ns = s_begin + s_lane; }
-          const bool has_next = nt < total_tiles && ns < s_end && (nt / p.heads) * A_TM + ns * L < p.M;
+          auto tile_m0 = [&](int tt) { return ((p.rev ? total_tiles - 1 - tt : tt) / p.heads) * A_TM; };
+          if (ns >= s_end || tile_m0(nt) + ns * L >= p.M) { nt = t + gridDim.x; ns = s_begin + s_lane; }
+          const bool has_next = nt < total_tiles && ns < s_end && tile_m0(nt) + ns * L < p.M;
           if (has_next) issue_kv(nt, ns, pf_buf ^ 1);
           if (has_next) asm volatile("cp.async.wait_group 1;" ::: "memory");
           else asm volatile("cp.async.wait_group 0;" ::: "memory");

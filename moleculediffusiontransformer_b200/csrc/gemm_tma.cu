@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
       const uint32_t tx = (uint32_t)(T_A_BYTES + BN * 128);
       int c = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int mt = t / n_tiles, nt = t - mt * n_tiles;
+        const int te = p.rev ? total_tiles - 1 - t : t;
+        const int mt = te / n_tiles, nt = te - mt * n_tiles;
         int b0, l0;
         if (p.L >= T_TM) { const int tps = p.L / T_TM; b0 = mt / tps; l0 = (mt - b0 * tps) * T_TM; }
         else { b0 = mt * p.Sb; l0 = 0; }
@@ -131,7 +132,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
     const bool active = half < ngroups;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int mt = t / n_tiles, nt = t - mt * n_tiles;
+      const int te = p.rev ? total_tiles - 1 - t : t;
+      const int mt = te / n_tiles, nt = te - mt * n_tiles;
       const int buf = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(&acc_full[buf], aphase);

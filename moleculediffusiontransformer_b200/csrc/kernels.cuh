@@ -155,10 +155,11 @@ struct GnApplyParams {
   void* out;   // normalised operand [B*L][C]
   void* raw;   // optional un-normalised operand copy (1x1 skip projection input) or null
   int B;
+  int rev;     // blocks walk the samples from the end (serpentine order)
 };
 cudaError_t launch_gn_apply(const GnApplyParams& p, int kind, cudaStream_t s);
 bool gn_apply_supported(int L, int C, int groups);
-struct LnApplyParams { const float* src; int C; float eps; void* out; long long rows; };
+struct LnApplyParams { const float* src; int C; float eps; void* out; long long rows; int rev; };
 cudaError_t launch_ln_apply(const LnApplyParams& p, int kind, cudaStream_t s);
 
 // ---- TMA-fed tcgen05 GEMM (gemm_tma.cu): both operands arrive by cp.async.bulk.tensor ------------------
@@ -174,6 +175,7 @@ struct TmaGemmParams {
   // a 32-row x 32-column epilogue block holds whole (sample, group) sets when gn_L | 32 and gn_cpg | 32 (gn_L = 0: off)
   int gn_L, gn_cpg; float gn_eps;
   const float* gn_aff; int gn_aff_stride; const int* gn_call;
+  int rev;                    // walk the row tiles from the end (serpentine order: start with what the producer wrote last)
 };
 // 128-byte CUtensorMap blobs (64-byte aligned) built on the host
 int make_tmap_act(void* map128, const void* base, int kind, int C, int L, long long samples);
@@ -196,6 +198,7 @@ struct GemmAttnParams {
   const void* kc; const void* kn;  // cross: conditioning K|V cache [B][nk][2 * heads * d] and the shared null-branch block
   int ldkv; long long kv_sample_stride; int n_cond; int nk;
   int kv_fp32;            // the cache pointers hold fp32 (always true in tf32 mode; bf16 mode may pass the fp32 cache)
+  int rev;                // walk the row tiles from the end (serpentine order)
 };
 bool gemm_attn_supported(int kind, int C, int L, int heads, int d, int cross, int nk_max);
 cudaError_t init_gemm_attn();

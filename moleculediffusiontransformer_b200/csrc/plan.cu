@@ -9,8 +9,10 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -113,6 +115,7 @@ struct mdt_plan {
   std::vector<void*> allocs;  // activation buffers
   size_t act_bytes = 0;
   long long launches = 0;
+  bool serpentine = false;
 
   // model dims
   int P = 0, L0 = 0, Hd = 0, F = 0, Bmax = 0, Beff_max = 0;
@@ -879,11 +882,60 @@ static void launch_gemm(mdt_plan& pl, const GemmParams& g, cudaStream_t s) {
   pl.launches++;
 }
 
+// MDT_OP_TIMES=1 (diagnostics; forces eager launches): per-op device time by shape, warm and back to back, printed when the
+// plan is destroyed.  ncu's per-launch times are cold-cache and serialised; this is the in-situ complement.
+struct OpTime { double ms = 0; long long n = 0; };
+static std::map<std::string, OpTime> g_op_times;
+static void dump_op_times();
+static bool op_times_on() {
+  static const bool on = [] { const bool v = getenv("MDT_OP_TIMES") != nullptr; if (v) atexit(dump_op_times); return v; }();
+  return on;
+}
+
+static std::string describe(const Op& op, int Beff) {
+  char b[160];
+  const char* h = op.half ? " half" : "";
+  switch (op.type) {
+    case OP_GEMM_TMA: snprintf(b, sizeof b, "gemm_tma  M=%d N=%d K=%dx%d L=%d bn=%d%s%s%s%s", Beff * op.rps, op.tg.N, op.tg.taps, op.tg.C, op.tg.L, op.tg.BN,
+                               op.tg.gn_L ? " +gn" : "", op.tg.res ? " +res" : "", op.tg.act ? " +act" : "", h); break;
+    case OP_GEMM_ATTN: snprintf(b, sizeof b, "gemm_attn %s M=%d C=%d L=%d%s", op.cross ? "cross" : "self", Beff * op.rps, op.gat.C, op.gat.L, h); break;
+    case OP_GEMM: snprintf(b, sizeof b, "gemm      M=%d N=%d K=%d taps=%d stride=%d%s", Beff * op.rps, op.g.N, op.g.K, op.g.a.taps, op.g.a.stride, h); break;
+    case OP_GN_APPLY: snprintf(b, sizeof b, "gn_apply  B=%d L=%d C=%d%s%s", Beff, op.ga.L, op.ga.c0 + op.ga.c1, op.ga.raw ? " +raw" : "", h); break;
+    case OP_LN_APPLY: snprintf(b, sizeof b, "ln_apply  rows=%d C=%d%s", Beff * op.rps, op.la.C, h); break;
+    case OP_GEMM_FF: snprintf(b, sizeof b, "gemm_ff   M=%d C=%d mid=%d%s", Beff * op.rps, op.gff.C, op.gff.mid, h); break;
+    default: snprintf(b, sizeof b, "other(type %d)%s", (int)op.type, h); break;
+  }
+  return b;
+}
+
+static void dump_op_times() {
+  if (g_op_times.empty()) return;
+  double tot = 0;
+  for (auto& kv : g_op_times) tot += kv.second.ms;
+  std::vector<std::pair<std::string, OpTime>> v(g_op_times.begin(), g_op_times.end());
+  std::sort(v.begin(), v.end(), [](const auto& a, const auto& b) { return a.second.ms > b.second.ms; });
+  fprintf(stderr, "[mdt] op times: %.3f ms total\n", tot);
+  for (auto& kv : v)
+    fprintf(stderr, "[mdt] %6.2f%% %9.3f ms n=%5lld avg=%8.1f us  %s\n", 100.0 * kv.second.ms / tot, kv.second.ms, kv.second.n,
+            1e3 * kv.second.ms / (double)kv.second.n, kv.first.c_str());
+  g_op_times.clear();
+}
+
 static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_cond, int n_ctx, cudaStream_t s) {
   if (getenv("MDT_NO_SHARED_PREFIX")) for (Op& op : prog) op.half = false;
   const int Beff_full = Beff;
+  const bool timed = op_times_on();
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (timed) { CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); }
+  // serpentine traversal: each of the four streaming kernels walks the batch in the opposite direction to the previous one,
+  // so a consumer starts on the rows its producer wrote last (still in L2) instead of the ones evicted first
+  const bool serp = pl.serpentine;
+  int rev = 0;
   for (Op& op : prog) {
     Beff = op.half ? n_cond : Beff_full;
+    if (timed) CK(cudaEventRecord(ev0, s));
+    const bool streams = op.type == OP_GEMM_TMA || op.type == OP_GEMM_ATTN || op.type == OP_GN_APPLY || op.type == OP_LN_APPLY;
+    rev = (serp && streams) ? (rev ^ 1) : 0;
     switch (op.type) {
       case OP_DUP_ROWS: {
         if (Beff_full > n_cond) {
@@ -901,17 +953,25 @@ static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_con
         if (op.cross) { a.nk = n_ctx; a.kv_sample_stride = (long long)n_ctx * a.ldkv; a.n_cond = n_cond; }
         CK(launch_attention(a, op.attn_kind, s)); pl.launches++; break;
       }
-      case OP_GN_APPLY: { GnApplyParams g = op.ga; g.B = Beff; CK(launch_gn_apply(g, pl.prec, s)); pl.launches++; break; }
-      case OP_LN_APPLY: { LnApplyParams l = op.la; l.rows = (long long)Beff * op.rps; CK(launch_ln_apply(l, pl.prec, s)); pl.launches++; break; }
+      case OP_GN_APPLY: { GnApplyParams g = op.ga; g.B = Beff; g.rev = rev; CK(launch_gn_apply(g, pl.prec, s)); pl.launches++; break; }
+      case OP_LN_APPLY: { LnApplyParams l = op.la; l.rows = (long long)Beff * op.rps; l.rev = rev; CK(launch_ln_apply(l, pl.prec, s)); pl.launches++; break; }
       case OP_GEMM_ATTN: {
-        GemmAttnParams g = op.gat; g.M = Beff * op.rps;
+        GemmAttnParams g = op.gat; g.M = Beff * op.rps; g.rev = rev;
         if (op.cross) { g.nk = n_ctx; g.kv_sample_stride = (long long)n_ctx * g.ldkv; g.n_cond = n_cond; }
         CK(launch_gemm_attn(op.tmA, op.tmB, g, pl.prec, s)); pl.launches++; break;
       }
       case OP_GEMM_FF: { GemmFFParams g = op.gff; g.M = Beff * op.rps; CK(launch_gemm_ff(op.tmA, op.tmB, op.tmC, g, pl.prec, s)); pl.launches++; break; }
-      case OP_GEMM_TMA: { TmaGemmParams g = op.tg; g.M = Beff * op.rps; CK(launch_gemm_tma(op.tmA, op.tmB, g, pl.prec, s)); pl.launches++; break; }
+      case OP_GEMM_TMA: { TmaGemmParams g = op.tg; g.M = Beff * op.rps; g.rev = rev; CK(launch_gemm_tma(op.tmA, op.tmB, g, pl.prec, s)); pl.launches++; break; }
       case OP_UPGATHER: CK(launch_upsample_gather(op.in0, op.in1, op.in2, op.out, Beff, op.i0, op.i1, op.i2, s)); pl.launches++; break;
       case OP_PERMUTE: CK(launch_patch_permute(op.in0, op.out, Beff, op.i0, op.i1, op.i2, op.i3, s)); pl.launches++; break;
+    }
+    if (timed) {
+      CK(cudaEventRecord(ev1, s));
+      CK(cudaEventSynchronize(ev1));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, ev0, ev1));
+      OpTime& t = g_op_times[describe(op, Beff)];
+      t.ms += ms; t.n++;
     }
     if (pl.taps_on && !op.tap.empty()) {
       CK(cudaStreamSynchronize(s));
@@ -920,6 +980,7 @@ static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_con
       CK(cudaMemcpy(dst.data(), op.tap_ptr, dst.size() * sizeof(float), cudaMemcpyDeviceToHost));
     }
   }
+  if (timed) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
 }
 
 static GemmParams dense(const float* A, int K, const float* W, const float* b, int N, int M, int act, float* C, bool silu_in) {
@@ -1067,7 +1128,9 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
     const int max_steps = cfg->max_timesteps > 1 ? cfg->max_timesteps : 256;
     pl->max_calls = 2 * (max_steps - 1);
     const char* eg = getenv("MDT_GRAPH");
-    pl->use_graph = !(eg && eg[0] == '0');
+    pl->use_graph = !(eg && eg[0] == '0') && !op_times_on();
+    const char* es = getenv("MDT_SERPENTINE");
+    pl->serpentine = !(es && es[0] == '0');
     size_t total = 0;
     for (int64_t i = 0; i < n_tensors; ++i) {
       if (!tensors[i].name || !tensors[i].data) raise(MDT_ERR_INVALID, "tensor %lld has a null field", (long long)i);
@@ -1099,6 +1162,7 @@ void mdt_plan_destroy(mdt_plan* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
   cudaDeviceSynchronize();
+  dump_op_times();
   for (auto& kv : pl->graphs) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : pl->allocs) cudaFree(p);
   if (pl->wslab) cudaFree(pl->wslab);

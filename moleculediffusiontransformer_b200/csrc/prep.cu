@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p, co
   float* data = sm;                                   // [spc][LC]
   float2* stats = reinterpret_cast<float2*>(sm + (size_t)spc * LC);  // [spc][groups]
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int b_first = blockIdx.x * spc;
+  const int b_first = (p.rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * spc;
   const int nb = min(spc, p.B - b_first);
   const int c4n = C >> 2;
   // ---- load (coalesced float4), concat + skip scale applied here
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) gn_apply_reg_kernel(const GnApplyParams p
   const int C = p.c0 + p.c1, L = p.L, cpg = C / p.groups, q4 = cpg >> 2;   // q4 = float4 per row segment
   const int lane = threadIdx.x & 31;
   const int gpw = 32 / seg;                                               // (sample, group) items per warp
-  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long warp_global = (long long)(p.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long item = warp_global * gpw + lane / seg;
   const int sl = lane % seg;
   const long long items = (long long)p.B * p.groups;
@@ -229,7 +229,7 @@ cudaError_t launch_gn_apply(const GnApplyParams& p, int kind, cudaStream_t s) {
 template <int KIND, int NV>   // NV = float4 per lane = C / 128 rounded up (register array size)
 __global__ void __launch_bounds__(256) ln_apply_kernel(const LnApplyParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + warp;
+  const long long row = (long long)(p.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 8 + warp;
   if (row >= p.rows) return;
   const int C = p.C;
   const float* src = p.src + (size_t)row * C;

@@ -1,0 +1,11 @@
+#!/bin/bash
+# A/B of an environment switch on the bench workload:  tools/ab.sh VAR   (runs VAR=0 and VAR=1, tf32, no CPU baseline)
+v=$1
+for x in 0 1 0 1; do
+  env $v=$x timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 0 2>/dev/null | python -c "
+import sys, json
+for l in sys.stdin:
+    l = l.strip()
+    if l.startswith('{'):
+        d = json.loads(l); print('$v=$x', d['value'], d['ms_per_step'])"
+done
