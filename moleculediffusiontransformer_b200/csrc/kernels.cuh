@@ -203,6 +203,10 @@ struct GemmAttnParams {
 bool gemm_attn_supported(int kind, int C, int L, int heads, int d, int cross, int nk_max);
 cudaError_t init_gemm_attn();
 cudaError_t launch_gemm_attn(const void* tmA, const void* tmB, const GemmAttnParams& p, int kind, cudaStream_t s);
+// same contract, attention core on tcgen05 too (gemm_attn_umma.cu): block-diagonal S = Q K^T and O = P V per 128-row tile
+bool gemm_attn_umma_supported(int kind, int C, int L, int heads, int d, int cross, int nk_max);
+cudaError_t init_gemm_attn_umma();
+cudaError_t launch_gemm_attn_umma(const void* tmA, const void* tmB, const GemmAttnParams& p, int kind, cudaStream_t s);
 
 // ---- fused FeedForward (gemm_ff.cu): Linear -> GELU -> Linear + residual, hidden activation stays on chip ---------
 struct GemmFFParams {

@@ -75,6 +75,7 @@ struct Op {
   alignas(64) unsigned char tmB[128];
   alignas(64) unsigned char tmC[128];
   bool cross = false;  // attention reads the precomputed conditioning K/V
+  bool umma_core = false;  // fused attention with the softmax-attention core on tcgen05 (gemm_attn_umma.cu)
   int cross_layer = -1;
   // upsample gather / permute
   const float* in0 = nullptr; const float* in1 = nullptr; const float* in2 = nullptr; float* out = nullptr;
@@ -351,6 +352,13 @@ struct Builder {
     const void* wop = tc_copy(dW32, (size_t)heads * BN * C);
     if (make_tmap_act(op.tmA, A, pl.prec, C, L, (long long)pl.Beff_max) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(attn activation) failed");
     if (make_tmap_weight(op.tmB, wop, pl.prec, (long long)C, heads * BN, BN) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(attn weight) failed");
+    // Attention core: tcgen05 (block-diagonal S / P V UMMAs over the whole 128-row tile, gemm_attn_umma.cu) or per-sample mma.sync
+    // (gemm_attn.cu).  Measured on the README model at B = 4096 (profiles/README.md): the UMMA core wins when the tile holds many short
+    // samples (L = 4: 84 vs 93 us) and loses when the per-sample mma.sync work is already one full m16 tile per warp (L = 16: 277 vs
+    // 220 us; its serial stage -> S -> softmax -> P V -> store chain is ~8 k cycles per tile).  MDT_UMMA_ATTN = 0 | auto | all.
+    const char* um = getenv("MDT_UMMA_ATTN");
+    const bool um_off = um && um[0] == '0', um_all = um && um[0] == 'a' && um[1] == 'l';
+    op.umma_core = !um_off && (um_all || L <= 8) && gemm_attn_umma_supported(pl.prec, C, L, heads, d, cross, pl.cfg.ctx_max_length);
     emit(prog, op);
   }
 
@@ -898,7 +906,7 @@ static std::string describe(const Op& op, int Beff) {
   switch (op.type) {
     case OP_GEMM_TMA: snprintf(b, sizeof b, "gemm_tma  M=%d N=%d K=%dx%d L=%d bn=%d%s%s%s%s", Beff * op.rps, op.tg.N, op.tg.taps, op.tg.C, op.tg.L, op.tg.BN,
                                op.tg.gn_L ? " +gn" : "", op.tg.res ? " +res" : "", op.tg.act ? " +act" : "", h); break;
-    case OP_GEMM_ATTN: snprintf(b, sizeof b, "gemm_attn %s M=%d C=%d L=%d%s", op.cross ? "cross" : "self", Beff * op.rps, op.gat.C, op.gat.L, h); break;
+    case OP_GEMM_ATTN: snprintf(b, sizeof b, "gemm_attn%s %s M=%d C=%d L=%d%s", op.umma_core ? "_umma" : "", op.cross ? "cross" : "self", Beff * op.rps, op.gat.C, op.gat.L, h); break;
     case OP_GEMM: snprintf(b, sizeof b, "gemm      M=%d N=%d K=%d taps=%d stride=%d%s", Beff * op.rps, op.g.N, op.g.K, op.g.a.taps, op.g.a.stride, h); break;
     case OP_GN_APPLY: snprintf(b, sizeof b, "gn_apply  B=%d L=%d C=%d%s%s", Beff, op.ga.L, op.ga.c0 + op.ga.c1, op.ga.raw ? " +raw" : "", h); break;
     case OP_LN_APPLY: snprintf(b, sizeof b, "ln_apply  rows=%d C=%d%s", Beff * op.rps, op.la.C, h); break;
@@ -958,7 +966,8 @@ static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_con
       case OP_GEMM_ATTN: {
         GemmAttnParams g = op.gat; g.M = Beff * op.rps; g.rev = rev;
         if (op.cross) { g.nk = n_ctx; g.kv_sample_stride = (long long)n_ctx * g.ldkv; g.n_cond = n_cond; }
-        CK(launch_gemm_attn(op.tmA, op.tmB, g, pl.prec, s)); pl.launches++; break;
+        CK(op.umma_core ? launch_gemm_attn_umma(op.tmA, op.tmB, g, pl.prec, s) : launch_gemm_attn(op.tmA, op.tmB, g, pl.prec, s));
+        pl.launches++; break;
       }
       case OP_GEMM_FF: { GemmFFParams g = op.gff; g.M = Beff * op.rps; CK(launch_gemm_ff(op.tmA, op.tmB, op.tmC, g, pl.prec, s)); pl.launches++; break; }
       case OP_GEMM_TMA: { TmaGemmParams g = op.tg; g.M = Beff * op.rps; g.rev = rev; CK(launch_gemm_tma(op.tmA, op.tmB, g, pl.prec, s)); pl.launches++; break; }
@@ -1121,6 +1130,7 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
     CK(init_gemm_tc());
     CK(init_gemm_tma());
     CK(init_gemm_attn());
+    CK(init_gemm_attn_umma());
     CK(init_gemm_ff());
     pl->cfg = *cfg; pl->device = device; pl->prec = cfg->precision;
     pl->P = cfg->in_channels; pl->L0 = cfg->length; pl->Hd = cfg->heads * cfg->head_features; pl->F = cfg->ctx_features;

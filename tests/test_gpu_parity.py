@@ -34,6 +34,25 @@ def test_unet_eval_vs_reference_fixture(name, prec, model_cache):
     assert orc.rel_l2(got, torch.from_numpy(golden(name)["net"])) < UNET_TOL[prec]
 
 
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("name", ["inv64_short_ctx_clamp", "inv64_cs7p5", "wide_cs7p5"])
+def test_unet_eval_umma_attention_core_everywhere(name, prec, model_cache, monkeypatch):
+    """The tcgen05 attention core is on by default only where it is faster (L <= 8); force it for every self-attention layer
+    (L = 16 / 32 too, and a batch that leaves stale rows in the last 128-row tile) and hold it to the same bounds."""
+    from moleculediffusiontransformer_b200.plan import SamplerPlan
+
+    monkeypatch.setenv("MDT_UMMA_ATTN", "all")
+    kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES[name]
+    m = model_cache(kind, kw, mseed)
+    seq, noise0, _ = make_inputs(name)
+    plan = SamplerPlan(m, "cuda:0", precision=prec, max_batch=8)
+    try:
+        got = plan.unet_forward(noise0, 0.37, seq, cond_scale=cs).cpu()
+    finally:
+        plan.close()
+    assert orc.rel_l2(got, torch.from_numpy(golden(name)["net"])) < UNET_TOL[prec]
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_sample_fp32_vs_reference_fixture(name, model_cache):
     kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES[name]
