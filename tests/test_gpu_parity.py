@@ -137,6 +137,33 @@ def test_shared_cfg_prefix_is_exact(prec, model_cache, monkeypatch):
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("umma", ["auto", "all"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+def test_stale_rows_of_a_poisoned_workspace_never_leak(prec, umma, model_cache, monkeypatch):
+    """The workspace is sized for the plan's maximum batch and every 128-row tile past the current batch holds whatever the
+    previous call left there.  Poison it (a call whose conditioning is NaN turns every activation into NaN), then run a small
+    ragged batch on the same plan: the result must be finite and bit-identical to the same rows run on a fresh plan."""
+    monkeypatch.setenv("MDT_UMMA_ATTN", umma)
+    kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES["inv64_cs7p5"]
+    torch.manual_seed(mseed)
+    import moleculediffusiontransformer_b200 as mdt
+    m = mdt.QMDiffusion(**kw).eval()                                     # private instance: its plan cache is part of the test
+    g = torch.Generator().manual_seed(11)
+    seq = torch.rand(37, n, generator=g) * 2 - 1
+    fresh = m.sample(seq[:5], "cuda:0", cond_scale=cs, timesteps=6, seed=3, precision=prec).cpu()
+    for p in m._plans.values():
+        p.close()
+    m._plans = {}
+    big = m.sample(seq, "cuda:0", cond_scale=cs, timesteps=6, seed=3, precision=prec).cpu()       # plan sized for 64 rows
+    assert torch.isfinite(big).all()
+    assert torch.equal(big[:5], fresh)                                   # rows do not depend on their batch mates
+    # (the sampler's x0 clamp maps NaN to a bound, so the returned tensor is finite; the activations behind it are not)
+    m.sample(torch.full((37, n), float("nan")), "cuda:0", cond_scale=cs, timesteps=3, seed=3, precision=prec)
+    again = m.sample(seq[:5], "cuda:0", cond_scale=cs, timesteps=6, seed=3, precision=prec).cpu()   # same (poisoned) plan
+    assert torch.isfinite(again).all()
+    assert torch.equal(again, fresh)
+
+
 def test_philox_noise_is_sharding_invariant_and_deterministic(model_cache):
     from moleculediffusiontransformer_b200 import ADPM2Sampler, KarrasSchedule
     from moleculediffusiontransformer_b200.plan import SamplerPlan
