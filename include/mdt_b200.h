@@ -166,6 +166,13 @@ int mdt_op_step_update(int which, const float* net_dev, float* x_dev, float* xmi
                        const float* noise_dev, const mdt_iter_scalars* it, float cond_scale, int64_t B,
                        int32_t P, int32_t L, int cfg, void* stream);
 
+/* Token ids -> text bytes on the device: replaces reverse_tokenize (generative.py:1069-1078; Keras sequences_to_texts on the argmax
+ * tokens of generative.py:1212-1213, then the spaces stripped).  lut_dev[256] maps a token id to its character (0: id has no
+ * vocabulary entry -- the padding id 0 always -- and is dropped).  out_dev[B][L] receives the compacted text zero padded to L,
+ * lengths_dev[B] (may be NULL) the number of characters. */
+int mdt_op_decode_tokens(const uint8_t* tokens_dev, const uint8_t* lut_dev, uint8_t* out_dev, int32_t* lengths_dev, int64_t B,
+                         int32_t L, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ EXPORTS = [
     "mdt_last_error", "mdt_abi_version", "mdt_device_count", "mdt_adpm2_scalars", "mdt_karras_sigmas",
     "mdt_plan_create", "mdt_plan_destroy", "mdt_plan_device_bytes", "mdt_plan_launch_count", "mdt_plan_sample",
     "mdt_plan_inpaint", "mdt_plan_unet_forward", "mdt_plan_enable_taps", "mdt_plan_read_tap", "mdt_op_linear", "mdt_op_step_update",
+    "mdt_op_decode_tokens",
 ]
 
 
@@ -83,6 +84,7 @@ def load() -> C.CDLL:
     lib.mdt_op_linear.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
     lib.mdt_op_step_update.argtypes = [C.c_int, vp, vp, vp, vp, vp, C.POINTER(MdtIterScalars), f32, i64, i32, i32,
                                        C.c_int, vp]
+    lib.mdt_op_decode_tokens.argtypes = [vp, vp, vp, vp, i64, i32, vp]
     if lib.mdt_abi_version() != MDT_ABI_VERSION:
         raise ImportError("libmdt_b200.so ABI version mismatch; rebuild the extension")
     _lib = lib

@@ -862,4 +862,35 @@ cudaError_t launch_inpaint(int mode, float* x, float* xin, const float* source, 
   return cudaGetLastError();
 }
 
+// ---- token ids -> text bytes (generative.py:1069-1078: Keras sequences_to_texts drops ids without a vocabulary entry -- padding id 0
+// among them -- and the reference strips the separating spaces).  One warp per row: ballot-compaction, zero padded to L, length out.
+__global__ void decode_tokens_kernel(const uint8_t* __restrict__ tokens, const uint8_t* __restrict__ lut, uint8_t* __restrict__ out,
+                                     int* __restrict__ lengths, long long B, int L) {
+  __shared__ uint8_t s_lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const uint8_t* src = tokens + row * L;
+  uint8_t* dst = out + row * L;
+  int base = 0;
+  for (int i0 = 0; i0 < L; i0 += 32) {
+    const int i = i0 + lane;
+    const uint8_t ch = i < L ? s_lut[src[i]] : (uint8_t)0;
+    const unsigned keep = __ballot_sync(0xffffffffu, ch != 0);
+    if (ch != 0) dst[base + __popc(keep & ((1u << lane) - 1u))] = ch;
+    base += __popc(keep);
+  }
+  for (int i = base + lane; i < L; i += 32) dst[i] = 0;
+  if (lane == 0 && lengths) lengths[row] = base;
+}
+
+cudaError_t launch_decode_tokens(const uint8_t* tokens, const uint8_t* lut, uint8_t* out, int* lengths, long long B, int L, cudaStream_t s) {
+  if (B <= 0 || L <= 0) return cudaSuccess;
+  const int wpb = 8;
+  decode_tokens_kernel<<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, s>>>(tokens, lut, out, lengths, B, L);
+  return cudaGetLastError();
+}
+
 }  // namespace mdt

@@ -137,6 +137,7 @@ cudaError_t launch_inpaint(int mode, float* x, float* xin, const float* source, 
                            float sigma, float c_in, unsigned long long seed, unsigned long long sample_offset, int stream, int B,
                            int P, int L, int cfg, float* out, cudaStream_t s);
 cudaError_t launch_set_u64x2(unsigned long long* dst, unsigned long long a, unsigned long long b, cudaStream_t s);
+cudaError_t launch_decode_tokens(const uint8_t* tokens, const uint8_t* lut, uint8_t* out, int* lengths, long long B, int L, cudaStream_t s);
 cudaError_t launch_set_int(int* dst, int v, cudaStream_t s);
 cudaError_t launch_add_int(int* dst, int v, cudaStream_t s);
 // (B,P,L) <-> token-major [B*L][P], with optional duplication into a second half (classifier-free null rows)

@@ -1448,4 +1448,14 @@ int mdt_op_step_update(int which, const float* net_dev, float* x_dev, float* xmi
   return 0;
 }
 
+int mdt_op_decode_tokens(const uint8_t* tokens_dev, const uint8_t* lut_dev, uint8_t* out_dev, int32_t* lengths_dev, int64_t B,
+                         int32_t L, void* stream) {
+  if (B < 0 || L < 0) return fail(MDT_ERR_INVALID, "negative size");
+  if (B == 0 || L == 0) return 0;
+  if (!tokens_dev || !lut_dev || !out_dev) return fail(MDT_ERR_INVALID, "null argument");
+  cudaError_t e = launch_decode_tokens(tokens_dev, lut_dev, out_dev, lengths_dev, (long long)B, L, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(MDT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 }  // extern "C"

@@ -92,3 +92,22 @@ def test_step_update_matches_reference_formulas(cfg):
                                   cs, B, P, L, cfg, None) == 0
     torch.cuda.synchronize()
     assert torch.allclose(xd.cpu(), xn_want, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (7, 64), (300, 64), (33, 45), (5, 200)])
+def test_decode_tokens_matches_reverse_tokenize(shape):
+    """mdt_op_decode_tokens against the restated reverse_tokenize (generative.py:1069-1078): padding in any position, ids outside
+    the vocabulary, empty rows, row lengths that are not a multiple of the warp size."""
+    from moleculediffusiontransformer_b200.screening import reverse_tokenize
+    from oracle.decode_oracle import reverse_tokenize as reverse_tokenize_oracle
+
+    vocab = {i + 1: ch for i, ch in enumerate("CNOF()=#123456[]+-Hcno")}
+    b, l = shape
+    g = torch.Generator().manual_seed(b * 1000 + l)
+    toks = torch.randint(0, 30, (b, l), generator=g, dtype=torch.int64)           # ids 23..29 have no entry
+    toks[torch.rand(b, l, generator=g) < 0.3] = 0                                  # padding anywhere, not only at the end
+    toks[0] = 0                                                                    # an all-padding row
+    toks = toks.to(torch.uint8)
+    got = reverse_tokenize(vocab, toks.to("cuda:0"))
+    assert got == reverse_tokenize_oracle(vocab, toks.numpy())
+    assert reverse_tokenize(vocab, torch.empty((0, l), dtype=torch.uint8, device="cuda:0")) == []

@@ -162,3 +162,26 @@ def test_tokens_to_forward_conditioning_matches_text_round_trip():
         ids = [t for t in row if t != 0][:6]
         want[i, : len(ids)] = torch.tensor(ids, dtype=torch.float32) / 21.0
     assert torch.equal(got, want)
+
+
+QM9_LIKE_VOCAB = {i + 1: ch for i, ch in enumerate("CNOF()=#123456[]+-Hcno")}   # char-level SMILES tokeniser, 22 ids like the paper's
+
+
+def test_decode_oracle_follows_keras_sequences_to_texts():
+    """reverse_tokenize (generative.py:1069-1078): ids without a vocabulary entry (padding 0 among them) vanish, spaces stripped."""
+    from oracle.decode_oracle import reverse_tokenize, sequences_to_texts
+
+    assert sequences_to_texts({1: "C", 2: "N"}, [[1, 2, 0, 1], [0, 0], [9, 1]]) == ["C N C", "", "C"]
+    x = np.array([[1, 1, 3, 0, 0], [0, 5, 0, 7, 200], [0, 0, 0, 0, 0]]) / 21.0
+    assert reverse_tokenize(QM9_LIKE_VOCAB, x, 21.0) == ["CCO", "(=", ""]
+
+
+def test_vocabulary_table_rejects_what_the_device_decoder_cannot_express():
+    from moleculediffusiontransformer_b200.screening import is_novel, vocabulary_table
+
+    lut = vocabulary_table(QM9_LIKE_VOCAB)
+    assert lut.shape == (256,) and lut[0] == 0 and chr(lut[1]) == "C" and lut[23] == 0
+    for bad in ({0: "C"}, {256: "C"}, {3: "Cl"}, {3: " "}, {3: "é"}):
+        with pytest.raises(ValueError):
+            vocabulary_table(bad)
+    assert is_novel(["CCO"], "CCN") and not is_novel(["CCO"], "CCO")
