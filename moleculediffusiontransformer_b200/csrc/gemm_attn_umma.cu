@@ -38,7 +38,7 @@ __device__ unsigned long long g_dbg[16];
 #endif
 
 constexpr int U_TM = 128;
-constexpr int U_STAGES = 2;
+constexpr int U_STAGES = 3;
 constexpr int U_ABYTES = U_TM * 128;
 constexpr int U_EPI_WARPS = 8;
 constexpr int U_THREADS = 64 + 32 * U_EPI_WARPS;
@@ -332,9 +332,9 @@ bool gemm_attn_umma_supported(int kind, int C, int L, int heads, int d, int cros
 }
 
 cudaError_t init_gemm_attn_umma() {
-  cudaError_t e = cudaFuncSetAttribute(tc::gemm_attn_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(tc::gemm_attn_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(tc::gemm_attn_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  return cudaFuncSetAttribute(tc::gemm_attn_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 
 static int g_sms_gu = 0;
