@@ -132,10 +132,13 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&
 template <int SK, int OK, int NT>
 __device__ __forceinline__ void attend_head_mma_nt(const typename SmemIO<SK>::T* qs, int sa, const typename SmemIO<SK>::T* ks,
                                                    const typename SmemIO<SK>::T* vs, int sb, int nq, int nk, float scale, void* out,
-                                                   size_t out_base, int ldo, int lane) {
+                                                   size_t out_base, int ldo, int lane, int blk = 0) {
+  // blk > 0 (power of two): the nq = nk <= 16 rows are 16 / blk short samples packed into one tile; a query sees only the keys of
+  // its own block (block-diagonal mask), so one m16 tile serves all of them
   typedef SmemIO<SK> IO;
   typedef SmemIO<OK> OUT;
   const int g = lane >> 2, q = lane & 3;
+  const int bm = blk > 0 ? ~(blk - 1) : 0;
   for (int i0 = 0; i0 < nq; i0 += 16) {
     const int r0 = min(i0 + g, nq - 1), r1 = min(i0 + g + 8, nq - 1);
     float sc[NT][4], sd[NT][4];   // two accumulator sets (even / odd k-steps): halves the dependent MMA chain
@@ -169,10 +172,11 @@ __device__ __forceinline__ void attend_head_mma_nt(const typename SmemIO<SK>::T*
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       const int j = t * 8 + 2 * q;
-      sc[t][0] = (j < nk) ? sc[t][0] * scale : -INFINITY;
-      sc[t][1] = (j + 1 < nk) ? sc[t][1] * scale : -INFINITY;
-      sc[t][2] = (j < nk) ? sc[t][2] * scale : -INFINITY;
-      sc[t][3] = (j + 1 < nk) ? sc[t][3] * scale : -INFINITY;
+      const bool in0 = ((j ^ g) & bm) == 0, in1 = ((j ^ (g + 8)) & bm) == 0;   // j and j + 1 share a block (blk >= 2)
+      sc[t][0] = (j < nk && in0) ? sc[t][0] * scale : -INFINITY;
+      sc[t][1] = (j + 1 < nk && in0) ? sc[t][1] * scale : -INFINITY;
+      sc[t][2] = (j < nk && in1) ? sc[t][2] * scale : -INFINITY;
+      sc[t][3] = (j + 1 < nk && in1) ? sc[t][3] * scale : -INFINITY;
       m0 = fmaxf(m0, fmaxf(sc[t][0], sc[t][1]));
       m1 = fmaxf(m1, fmaxf(sc[t][2], sc[t][3]));
     }
@@ -226,6 +230,108 @@ __device__ __forceinline__ void attend_head_mma(const typename SmemIO<SK>::T* qs
   else if (nk <= 16) attend_head_mma_nt<SK, OK, 2>(qs, sa, ks, vs, sb, nq, nk, scale, out, out_base, ldo, lane);
   else if (nk <= 32) attend_head_mma_nt<SK, OK, 4>(qs, sa, ks, vs, sb, nq, nk, scale, out, out_base, ldo, lane);
   else attend_head_mma_nt<SK, OK, 8>(qs, sa, ks, vs, sb, nq, nk, scale, out, out_base, ldo, lane);
+}
+
+// ---- packed cross-attention for short query blocks ----------------------------------------------------------------------------
+// LQ = 4 or 8 queries per sample: G = 16 / LQ consecutive samples share one m16 tile (rows t * LQ .. of sample t), every sample
+// brings its own context K / V.  K and V come straight from global memory in B-fragment order (kv_fragment_pack_kernel in
+// kernels.cu: one coalesced 8-byte load per lane per fragment, no shared-memory staging); the G score blocks are independent MMA
+// chains, the softmax runs once on the rows' own blocks, and P V accumulates the G samples into one output tile (rows of other
+// samples enter as zeros).  nk <= 16.  kf[t] points at the 1024-uint2 [K | V] block of sample t and this tile's head.
+template <int OK, int LQ>
+__device__ __forceinline__ void attend_packed_cross(const float* qs, int sa, const uint2* const (&kf)[16 / LQ], int nk, float scale,
+                                                    void* out, size_t out_base, int ldo, int rows_valid, int lane) {
+  typedef SmemIO<OK> OUT;
+  constexpr int G = 16 / LQ;
+  const int g = lane >> 2, q = lane & 3;
+  float sc[G][2][4];
+#pragma unroll
+  for (int t = 0; t < G; ++t)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) { sc[t][nt][0] = 0.f; sc[t][nt][1] = 0.f; sc[t][nt][2] = 0.f; sc[t][nt][3] = 0.f; }
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    uint32_t a[4];
+    a[0] = __float_as_uint(qs[g * sa + ks * 8 + q]);
+    a[1] = __float_as_uint(qs[(g + 8) * sa + ks * 8 + q]);
+    a[2] = __float_as_uint(qs[g * sa + ks * 8 + q + 4]);
+    a[3] = __float_as_uint(qs[(g + 8) * sa + ks * 8 + q + 4]);
+#pragma unroll
+    for (int t = 0; t < G; ++t)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const uint2 b = __ldg(kf[t] + (ks * 2 + nt) * 32 + lane);
+        mma_tf32_16x8x8(sc[t][nt], a, b.x, b.y);
+      }
+  }
+  // row g belongs to sample t0 = g / LQ, row g + 8 to sample t1 = (g + 8) / LQ: pick their score blocks
+  const int t0 = g / LQ, t1 = (g + 8) / LQ;
+  float s0[2][2], s1[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    if (LQ == 4) {
+      s0[nt][0] = (g < 4) ? sc[0][nt][0] : sc[G > 1 ? 1 : 0][nt][0]; s0[nt][1] = (g < 4) ? sc[0][nt][1] : sc[G > 1 ? 1 : 0][nt][1];
+      s1[nt][0] = (g < 4) ? sc[G > 2 ? 2 : 0][nt][2] : sc[G > 3 ? 3 : 0][nt][2];
+      s1[nt][1] = (g < 4) ? sc[G > 2 ? 2 : 0][nt][3] : sc[G > 3 ? 3 : 0][nt][3];
+    } else {
+      s0[nt][0] = sc[0][nt][0]; s0[nt][1] = sc[0][nt][1];
+      s1[nt][0] = sc[G > 1 ? 1 : 0][nt][2]; s1[nt][1] = sc[G > 1 ? 1 : 0][nt][3];
+    }
+  }
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    const int j = nt * 8 + 2 * q;
+    s0[nt][0] = (j < nk) ? s0[nt][0] * scale : -INFINITY; s0[nt][1] = (j + 1 < nk) ? s0[nt][1] * scale : -INFINITY;
+    s1[nt][0] = (j < nk) ? s1[nt][0] * scale : -INFINITY; s1[nt][1] = (j + 1 < nk) ? s1[nt][1] * scale : -INFINITY;
+    m0 = fmaxf(m0, fmaxf(s0[nt][0], s0[nt][1]));
+    m1 = fmaxf(m1, fmaxf(s1[nt][0], s1[nt][1]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    s0[nt][0] = __expf(s0[nt][0] - m0); s0[nt][1] = __expf(s0[nt][1] - m0);
+    s1[nt][0] = __expf(s1[nt][0] - m1); s1[nt][1] = __expf(s1[nt][1] - m1);
+    z0 += s0[nt][0] + s0[nt][1]; z1 += s1[nt][0] + s1[nt][1];
+  }
+  z0 += __shfl_xor_sync(0xffffffffu, z0, 1); z0 += __shfl_xor_sync(0xffffffffu, z0, 2);
+  z1 += __shfl_xor_sync(0xffffffffu, z1, 1); z1 += __shfl_xor_sync(0xffffffffu, z1, 2);
+  const float inv0 = 1.0f / z0, inv1 = 1.0f / z1;
+  uint32_t p0[2][2], p1[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    p0[nt][0] = tc::to_tf32(s0[nt][0] * inv0); p0[nt][1] = tc::to_tf32(s0[nt][1] * inv0);
+    p1[nt][0] = tc::to_tf32(s1[nt][0] * inv1); p1[nt][1] = tc::to_tf32(s1[nt][1] * inv1);
+  }
+  float oc[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) { oc[n][0] = 0.f; oc[n][1] = 0.f; oc[n][2] = 0.f; oc[n][3] = 0.f; }
+#pragma unroll
+  for (int t = 0; t < G; ++t) {
+    const bool own0 = t0 == t, own1 = t1 == t;
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {
+      uint32_t a[4];
+      a[0] = own0 ? p0[kt][0] : 0u;   // (row g,     key 8 kt + 2q)
+      a[1] = own1 ? p1[kt][0] : 0u;   // (row g + 8, key 8 kt + 2q)
+      a[2] = own0 ? p0[kt][1] : 0u;   // (row g,     key 8 kt + 2q + 1)
+      a[3] = own1 ? p1[kt][1] : 0u;   // (row g + 8, key 8 kt + 2q + 1)
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const uint2 b = __ldg(kf[t] + 512 + (kt * 8 + n) * 32 + lane);
+        mma_tf32_16x8x8(oc[n], a, b.x, b.y);
+      }
+    }
+  }
+  const bool ok0 = g < rows_valid, ok1 = g + 8 < rows_valid;
+  const size_t o0 = out_base + (size_t)g * ldo + 2 * q, o1 = o0 + (size_t)8 * ldo;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    if (ok0) OUT::st2(out, o0 + n * 8, oc[n][0], oc[n][1]);
+    if (ok1) OUT::st2(out, o1 + n * 8, oc[n][2], oc[n][3]);
+  }
 }
 
 }  // namespace mdt

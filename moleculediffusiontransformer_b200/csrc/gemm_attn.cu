@@ -29,11 +29,15 @@ constexpr int A_THREADS = 64 + 32 * A_EPI_WARPS;
 #endif
 constexpr int A_LD = 68;   // staged q/k/v row stride in floats (64 + 4: conflict-free fragment loads)
 
-template <int KIND>
+// MODE selects the attention core compiled into the epilogue (one path per instantiation keeps each within the register budget):
+//   0 self, one sample per warp pass      1 self, 16 / L short samples packed into one block-diagonal m16 tile (L <= 8)
+//   2 cross, K / V staged with cp.async   3 cross, K / V fragments straight from the fragment-ordered cache (n_ctx <= 16)
+template <int KIND, int MODE>
 __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const GemmAttnParams p, const uint32_t idesc) {
   constexpr int KCH = (KIND == 1) ? 32 : 64;
+  constexpr bool CROSS = MODE >= 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B operand tiles need 1024-byte alignment
   __shared__ __align__(8) uint64_t full_bar[A_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[A_STAGES];
@@ -45,12 +49,12 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int BN = p.cross ? p.d : 3 * p.d;
+  const int BN = CROSS ? p.d : 3 * p.d;
   const int b_bytes = BN * 128;
   const int stage_bytes = A_ABYTES + ((b_bytes + 1023) & ~1023);
   const int m_tiles = (p.M + A_TM - 1) / A_TM;
   const int total_tiles = m_tiles * p.heads;
-  const uint32_t tmem_cols = p.cross ? 128u : 512u;   // two accumulators of BN columns
+  const uint32_t tmem_cols = CROSS ? 128u : 512u;   // two accumulators of BN columns
   float* Qs = reinterpret_cast<float*>(smem + A_STAGES * stage_bytes);
   float* Ks = Qs + A_TM * A_LD;                       // self: staged k rows; cross: per-warp K scratch base
   float* Vs = Ks + A_TM * A_LD;
@@ -161,6 +165,11 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
         uint32_t v[32];
         const int col0 = half * cols_per_warp + cc;
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0), v);
+        if (m0 + row >= p.M) {
+          // rows past the batch are in bounds for the TMA box and hold stale data; the packed tiles multiply them by P = 0
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
         float* dst = (col0 < 64 ? Qs : (col0 < 128 ? Ks : Vs)) + (size_t)row * A_LD + (col0 & 63);
         if (col0 < 64) {
           // only q carries a bias here: the k bias shifts every score of a query equally (cancels in the softmax) and
@@ -191,12 +200,44 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
       if (quad_local) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       else asm volatile("bar.sync 1, 256;" ::: "memory");
       if (lane == 0) mbar_arrive(&acc_empty[buf]);             // the accumulator may be overwritten now
+      if constexpr (MODE == 3) {
+        // packed path (L = 4, 8, 16): this warp's 16 rows = 16 / L whole samples in one m16 tile, K / V fragments straight from global
+        const int r16 = q * 32 + half * 16;
+        const int mrow = m0 + r16;
+        if (mrow < p.M) {
+          const int bs = mrow / L;
+          const size_t ob = (size_t)mrow * p.ldo + (size_t)h * p.d;
+          const int rows_valid = min(16, p.M - mrow);
+          auto block_of = [&](int t) {
+            const int b = (mrow + t * L < p.M) ? bs + t : bs;            // samples past the batch: any valid block, rows not stored
+            const bool nul = p.kn && b >= p.n_cond;
+            return reinterpret_cast<const uint2*>(nul ? p.kvf_n : p.kvf_c) + ((nul ? (size_t)0 : (size_t)b * p.heads) + h) * 1024;
+          };
+          if (L == 4) {
+            const uint2* const kf[4] = {block_of(0), block_of(1), block_of(2), block_of(3)};
+            attend_packed_cross<KIND, 4>(Qs + (size_t)r16 * A_LD, A_LD, kf, p.nk, p.scale, p.att, ob, p.ldo, rows_valid, lane);
+          } else if (L == 8) {
+            const uint2* const kf[2] = {block_of(0), block_of(1)};
+            attend_packed_cross<KIND, 8>(Qs + (size_t)r16 * A_LD, A_LD, kf, p.nk, p.scale, p.att, ob, p.ldo, rows_valid, lane);
+          } else {
+            const uint2* const kf[1] = {block_of(0)};
+            attend_packed_cross<KIND, 16>(Qs + (size_t)r16 * A_LD, A_LD, kf, p.nk, p.scale, p.att, ob, p.ldo, rows_valid, lane);
+          }
+        }
+      } else if constexpr (MODE == 1) {
+        // short samples (L <= 8): this warp's 16 staged rows = 16 / L samples as one block-diagonal 16 x 16 attention
+        const int r16 = q * 32 + half * 16;
+        const int mrow = m0 + r16;
+        if (mrow < p.M)
+          attend_head_mma_nt<1, KIND, 2>(Qs + (size_t)r16 * A_LD, A_LD, Ks + (size_t)r16 * A_LD, Vs + (size_t)r16 * A_LD, A_LD,
+                                         min(16, p.M - mrow), 16, p.scale, p.att, (size_t)mrow * p.ldo + (size_t)h * p.d, p.ldo, lane, L);
+      } else
       for (int s = s_begin + s_lane; s < s_end; s += s_step) {
         const int mrow = m0 + s * L;
         if (mrow >= p.M) break;
         const size_t ob = (size_t)mrow * p.ldo + (size_t)h * p.d;
         if (MDT_ATTN_SKIP_MATH) {
-        } else if (!p.cross) {
+        } else if constexpr (!CROSS) {
           attend_head_mma<1, KIND>(Qs + (size_t)s * L * A_LD, A_LD, Ks + (size_t)s * L * A_LD, Vs + (size_t)s * L * A_LD, A_LD, L, L,
                                    p.scale, p.att, ob, p.ldo, lane);
         } else if (KIND == 1 || p.kv_fp32) {
@@ -247,7 +288,8 @@ static size_t gemm_attn_smem(const GemmAttnParams& p, int nk_max) {
   const int BN = p.cross ? p.d : 3 * p.d;
   const size_t stage = tc::A_ABYTES + (((size_t)BN * 128 + 1023) & ~(size_t)1023);
   size_t stg = (size_t)tc::A_TM * tc::A_LD * 4;   // Qs
-  if (p.cross) stg += (size_t)tc::A_EPI_WARPS * 2 * 2 * nk_max * tc::A_LD * 4;   // per warp: two [K | V] scratch buffers
+  if (p.cross && p.kvf_c) {}                                                       // packed path: K / V fragments come from global
+  else if (p.cross) stg += (size_t)tc::A_EPI_WARPS * 2 * 2 * nk_max * tc::A_LD * 4;   // per warp: two [K | V] scratch buffers
   else stg += 2 * (size_t)tc::A_TM * tc::A_LD * 4;
   return tc::A_STAGES * stage + stg + 1024;
 }
@@ -260,10 +302,21 @@ bool gemm_attn_supported(int kind, int C, int L, int heads, int d, int cross, in
   return gemm_attn_smem(p, cross ? nk_max : 0) <= 220 * 1024 && (!cross || nk_max <= 64);
 }
 
+typedef void (*GemmAttnKernel)(const CUtensorMap, const CUtensorMap, const GemmAttnParams, const uint32_t);
+static GemmAttnKernel gemm_attn_variant(int kind, int mode) {
+  static const GemmAttnKernel tab[2][4] = {
+      {tc::gemm_attn_kernel<1, 0>, tc::gemm_attn_kernel<1, 1>, tc::gemm_attn_kernel<1, 2>, tc::gemm_attn_kernel<1, 3>},
+      {tc::gemm_attn_kernel<2, 0>, tc::gemm_attn_kernel<2, 1>, tc::gemm_attn_kernel<2, 2>, tc::gemm_attn_kernel<2, 3>}};
+  return tab[kind == 1 ? 0 : 1][mode];
+}
+
 cudaError_t init_gemm_attn() {
-  cudaError_t e = cudaFuncSetAttribute(tc::gemm_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(tc::gemm_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  for (int kind = 1; kind <= 2; ++kind)
+    for (int mode = 0; mode < 4; ++mode) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_attn_variant(kind, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (e != cudaSuccess) return e;
+    }
+  return cudaSuccess;
 }
 
 static int g_sms_ga = 0;
@@ -284,8 +337,8 @@ cudaError_t launch_gemm_attn(const void* tmA, const void* tmB, const GemmAttnPar
   const unsigned grid = (unsigned)(tiles < g_sms_ga ? tiles : g_sms_ga);
   const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(tmA);
   const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(tmB);
-  if (kind == 1) tc::gemm_attn_kernel<1><<<grid, tc::A_THREADS, smem, s>>>(a, b, p, idesc);
-  else tc::gemm_attn_kernel<2><<<grid, tc::A_THREADS, smem, s>>>(a, b, p, idesc);
+  const int mode = p.cross ? (p.kvf_c ? 3 : 2) : ((p.pack_self && p.L <= 8) ? 1 : 0);
+  gemm_attn_variant(kind, mode)<<<grid, tc::A_THREADS, smem, s>>>(a, b, p, idesc);
   return cudaGetLastError();
 }
 

@@ -862,6 +862,45 @@ cudaError_t launch_inpaint(int mode, float* x, float* xin, const float* source, 
   return cudaGetLastError();
 }
 
+// ---- cross-attention K/V cache in mma.sync B-fragment order (gemm_attn.cu, packed path) ------------------------------------------
+// out[(b * heads + h)][which = K|V][f = 0..15][lane] = uint2(b0, b1), the two B-fragment registers lane `lane` feeds to
+// mma.m16n8k8 for fragment f:   K: f = kstep * 2 + ntile   b0 = K[8 ntile + g][8 kstep + q],  b1 = K[..][8 kstep + q + 4]
+//                               V: f = ktile * 8 + ntile   b0 = V[8 ktile + 2q][8 ntile + g], b1 = V[8 ktile + 2q + 1][8 ntile + g]
+// (g = lane / 4, q = lane % 4; the V key permutation matches the P -> A-fragment reuse in attn_math.cuh).  Keys >= nk read as 0.
+// Values are rounded to tf32.  One 256-byte coalesced load per fragment replaces the cp.async staging + shared-memory fragment loads.
+__global__ void kv_fragment_pack_kernel(const float* __restrict__ kv, uint2* __restrict__ out, long long B, int nk, int heads, int d) {
+  const long long bh = blockIdx.x;
+  const long long b = bh / heads;
+  const int h = (int)(bh - b * heads);
+  if (b >= B) return;
+  const int ldkv = 2 * heads * d;
+  const float* base = kv + (size_t)b * nk * ldkv + (size_t)h * d;
+  for (int idx = threadIdx.x; idx < 1024; idx += blockDim.x) {
+    const int which = idx >> 9, f = (idx >> 5) & 15, lane = idx & 31, g = lane >> 2, q = lane & 3;
+    float b0 = 0.f, b1 = 0.f;
+    if (which == 0) {
+      const int key = (f & 1) * 8 + g, c0 = (f >> 1) * 8 + q;
+      if (key < nk) { b0 = base[(size_t)key * ldkv + c0]; b1 = base[(size_t)key * ldkv + c0 + 4]; }
+    } else {
+      const int j0 = (f >> 3) * 8 + 2 * q, col = (f & 7) * 8 + g;
+      const float* v = base + heads * d;
+      if (j0 < nk) b0 = v[(size_t)j0 * ldkv + col];
+      if (j0 + 1 < nk) b1 = v[(size_t)(j0 + 1) * ldkv + col];
+    }
+    uint32_t r0, r1;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(b0));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(b1));
+    out[(size_t)bh * 1024 + idx] = make_uint2(r0, r1);
+  }
+}
+
+cudaError_t launch_kv_fragment_pack(const float* kv, void* out, long long B, int nk, int heads, int d, cudaStream_t s) {
+  if (B <= 0) return cudaSuccess;
+  if (d != 64 || nk > 16 || nk < 1) return cudaErrorInvalidValue;
+  kv_fragment_pack_kernel<<<(unsigned)(B * heads), 256, 0, s>>>(kv, reinterpret_cast<uint2*>(out), B, nk, heads, d);
+  return cudaGetLastError();
+}
+
 // ---- token ids -> text bytes (generative.py:1069-1078: Keras sequences_to_texts drops ids without a vocabulary entry -- padding id 0
 // among them -- and the reference strips the separating spaces).  One warp per row: ballot-compaction, zero padded to L, length out.
 __global__ void decode_tokens_kernel(const uint8_t* __restrict__ tokens, const uint8_t* __restrict__ lut, uint8_t* __restrict__ out,

@@ -137,6 +137,7 @@ cudaError_t launch_inpaint(int mode, float* x, float* xin, const float* source, 
                            float sigma, float c_in, unsigned long long seed, unsigned long long sample_offset, int stream, int B,
                            int P, int L, int cfg, float* out, cudaStream_t s);
 cudaError_t launch_set_u64x2(unsigned long long* dst, unsigned long long a, unsigned long long b, cudaStream_t s);
+cudaError_t launch_kv_fragment_pack(const float* kv, void* out, long long B, int nk, int heads, int d, cudaStream_t s);
 cudaError_t launch_decode_tokens(const uint8_t* tokens, const uint8_t* lut, uint8_t* out, int* lengths, long long B, int L, cudaStream_t s);
 cudaError_t launch_set_int(int* dst, int v, cudaStream_t s);
 cudaError_t launch_add_int(int* dst, int v, cudaStream_t s);
@@ -199,6 +200,8 @@ struct GemmAttnParams {
   const void* kc; const void* kn;  // cross: conditioning K|V cache [B][nk][2 * heads * d] and the shared null-branch block
   int ldkv; long long kv_sample_stride; int n_cond; int nk;
   int kv_fp32;            // the cache pointers hold fp32 (always true in tf32 mode; bf16 mode may pass the fp32 cache)
+  int pack_self;          // self, L <= 8: 16 / L samples per m16 tile with a block-diagonal mask
+  const void* kvf_c; const void* kvf_n;   // cross, L <= 8: fragment-ordered tf32 K/V cache (kv_fragment_pack_kernel), 8 KB per (sample, head); null = off
   int rev;                // walk the row tiles from the end (serpentine order)
 };
 bool gemm_attn_supported(int kind, int C, int L, int heads, int d, int cross, int nk_max);

@@ -103,6 +103,8 @@ struct CrossLayer {
   float* kv_null;                      // [n_ctx_max][2*Hd]
   void* kv_cond_op = nullptr;          // operand-dtype copies read by the attention kernel in the tensor-core modes
   void* kv_null_op = nullptr;
+  void* kvf_cond = nullptr;            // fragment-ordered tf32 copies for the packed cross-attention path (L <= 8), 8 KB per (sample, head)
+  void* kvf_null = nullptr;
 };
 
 struct mdt_plan {
@@ -341,7 +343,7 @@ struct Builder {
 
   // fused per-head projection + attention (gemm_attn.cu); dW32 = [heads * BN][C] fp32 on the device, head-major
   void emit_gemm_attn(std::vector<Op>& prog, const void* A, int C, int L, const float* dW32, const float* bias, int cross,
-                      int cross_layer, const void* kc, const void* kn) {
+                      int cross_layer, const void* kc, const void* kn, const void* kvf_c = nullptr, const void* kvf_n = nullptr) {
     Op op; op.type = OP_GEMM_ATTN; op.rps = L; op.cross = cross != 0; op.cross_layer = cross_layer;
     const int kch = pl.prec == MDT_PREC_TF32 ? 32 : 64;
     const int heads = pl.cfg.heads, d = pl.cfg.head_features, BN = cross ? d : 3 * d;
@@ -349,16 +351,20 @@ struct Builder {
     g.M = 0; g.heads = heads; g.d = d; g.kchunks = C / kch; g.C = C; g.L = L; g.Sb = 128 / L; g.cross = cross;
     g.bias = bias; g.scale = 1.0f / sqrtf((float)d); g.att = pl.att; g.ldo = heads * d;
     g.kc = kc; g.kn = kn; g.ldkv = 2 * heads * d; g.kv_sample_stride = 0; g.n_cond = 0; g.nk = L; g.kv_fp32 = 1;
+    g.kvf_c = kvf_c; g.kvf_n = kvf_n;
     const void* wop = tc_copy(dW32, (size_t)heads * BN * C);
     if (make_tmap_act(op.tmA, A, pl.prec, C, L, (long long)pl.Beff_max) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(attn activation) failed");
     if (make_tmap_weight(op.tmB, wop, pl.prec, (long long)C, heads * BN, BN) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(attn weight) failed");
-    // Attention core: tcgen05 (block-diagonal S / P V UMMAs over the whole 128-row tile, gemm_attn_umma.cu) or per-sample mma.sync
-    // (gemm_attn.cu).  Measured on the README model at B = 4096 (profiles/README.md): the UMMA core wins when the tile holds many short
-    // samples (L = 4: 84 vs 93 us) and loses when the per-sample mma.sync work is already one full m16 tile per warp (L = 16: 277 vs
-    // 220 us; its serial stage -> S -> softmax -> P V -> store chain is ~8 k cycles per tile).  MDT_UMMA_ATTN = 0 | auto | all.
+    // Attention core: per-sample / packed mma.sync (gemm_attn.cu, default) or tcgen05 (block-diagonal S / P V UMMAs over the whole
+    // 128-row tile, gemm_attn_umma.cu).  Measured on the README model at B = 4096 (profiles/README.md): the UMMA core's serial
+    // stage -> S -> softmax -> P V -> store chain is ~8 k cycles per tile, which loses at L = 16 (277 vs 210 us) and, since the
+    // mma.sync kernel packs 16 / L short samples into one block-diagonal m16 tile, at L = 4 too (78 vs 69 us).  It stays available:
+    // MDT_UMMA_ATTN = short (L <= 8) | all.
     const char* um = getenv("MDT_UMMA_ATTN");
-    const bool um_off = um && um[0] == '0', um_all = um && um[0] == 'a' && um[1] == 'l';
-    op.umma_core = !um_off && (um_all || L <= 8) && gemm_attn_umma_supported(pl.prec, C, L, heads, d, cross, pl.cfg.ctx_max_length);
+    const bool um_all = um && um[0] == 'a' && um[1] == 'l', um_short = um && um[0] == 's';
+    op.umma_core = (um_all || (um_short && L <= 8)) && gemm_attn_umma_supported(pl.prec, C, L, heads, d, cross, pl.cfg.ctx_max_length);
+    const char* ps = getenv("MDT_PACK_SELF");
+    g.pack_self = (!cross && L >= 2 && L <= 8 && !(ps && ps[0] == '0')) ? 1 : 0;
     emit(prog, op);
   }
 
@@ -588,8 +594,18 @@ struct Builder {
         if (fuse_cross) {
           emit_ln_apply(prog, t, C, L, tn);
           // the fused kernel streams fp32 K/V with cp.async in both tensor-core modes (tf32: rounded copy, bf16: the fp32 cache)
+          // short query blocks (L = 4, 8) with a context of at most 16 rows: 16 / L samples per m16 tile, K / V from a fragment-ordered cache
+          const char* np = getenv("MDT_NO_PACKED_CROSS");
+          const char* ml = getenv("MDT_PACKED_CROSS_MAXL");
+          const int maxl = ml ? atoi(ml) : 16;
+          if ((L == 4 || L == 8 || L == 16) && L <= maxl && pl.cfg.ctx_max_length <= 16 && d == 64 && !(np && np[0] != '0')) {
+            CrossLayer& clr = pl.cross[layer];
+            clr.kvf_cond = dalloc((size_t)pl.Bmax * heads * 2048);
+            clr.kvf_null = dalloc((size_t)heads * 2048);
+            cl = clr;
+          }
           emit_gemm_attn(prog, tn, C, L, d_wq, d_bq, 1, layer, pl.prec == MDT_PREC_TF32 ? cl.kv_cond_op : (void*)cl.kv_cond,
-                         pl.prec == MDT_PREC_TF32 ? cl.kv_null_op : (void*)cl.kv_null);
+                         pl.prec == MDT_PREC_TF32 ? cl.kv_null_op : (void*)cl.kv_null, cl.kvf_cond, cl.kvf_null);
         } else if (fast) {
           emit_ln_apply(prog, t, C, L, tn);
           emit_gemm_tma(prog, tn, C, L, 1, d_wq, d_bq, Hd, 0, nullptr, nullptr, pl.qc);
@@ -1036,11 +1052,13 @@ static void run_context(mdt_plan& pl, const float* cond_dev, int Bc, int n_ctx, 
     g.a.stats = pl.emb_stats; g.a.stats_mode = 1;
     CK(launch_gemm_fp32(g, s)); pl.launches++;
     if (cl.kv_cond_op) { CK(convert_weights_tc(cl.kv_cond, cl.kv_cond_op, (long long)Bc * n_ctx * 2 * Hd, pl.prec, s)); pl.launches++; }
+    if (cl.kvf_cond) { CK(launch_kv_fragment_pack(cl.kv_cond, cl.kvf_cond, Bc, n_ctx, c.heads, c.head_features, s)); pl.launches++; }
     if (cfg) {
       GemmParams gn = dense(pl.w_null_emb, F, cl.wkv, cl.bkv, 2 * Hd, n_ctx, 0, cl.kv_null, false);
       gn.a.stats = pl.emb_null_stats; gn.a.stats_mode = 1;
       CK(launch_gemm_fp32(gn, s)); pl.launches++;
       if (cl.kv_null_op) { CK(convert_weights_tc(cl.kv_null, cl.kv_null_op, (long long)n_ctx * 2 * Hd, pl.prec, s)); pl.launches++; }
+      if (cl.kvf_null) { CK(launch_kv_fragment_pack(cl.kv_null, cl.kvf_null, 1, n_ctx, c.heads, c.head_features, s)); pl.launches++; }
     }
   }
 }

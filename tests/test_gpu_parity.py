@@ -37,8 +37,8 @@ def test_unet_eval_vs_reference_fixture(name, prec, model_cache):
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
 @pytest.mark.parametrize("name", ["inv64_short_ctx_clamp", "inv64_cs7p5", "wide_cs7p5"])
 def test_unet_eval_umma_attention_core_everywhere(name, prec, model_cache, monkeypatch):
-    """The tcgen05 attention core is on by default only where it is faster (L <= 8); force it for every self-attention layer
-    (L = 16 / 32 too, and a batch that leaves stale rows in the last 128-row tile) and hold it to the same bounds."""
+    """The tcgen05 attention core is opt-in (the packed mma.sync core is faster on this model); force it for every self-attention
+    layer (L = 4 .. 32, and a batch that leaves stale rows in the last 128-row tile) and hold it to the same bounds."""
     from moleculediffusiontransformer_b200.plan import SamplerPlan
 
     monkeypatch.setenv("MDT_UMMA_ATTN", "all")
@@ -137,7 +137,7 @@ def test_shared_cfg_prefix_is_exact(prec, model_cache, monkeypatch):
     assert torch.equal(outs[0], outs[1])
 
 
-@pytest.mark.parametrize("umma", ["auto", "all"])
+@pytest.mark.parametrize("umma", ["0", "all"])
 @pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
 def test_stale_rows_of_a_poisoned_workspace_never_leak(prec, umma, model_cache, monkeypatch):
     """The workspace is sized for the plan's maximum batch and every 128-row tile past the current batch holds whatever the
