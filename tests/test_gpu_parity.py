@@ -53,6 +53,29 @@ def test_unet_eval_umma_attention_core_everywhere(name, prec, model_cache, monke
     assert orc.rel_l2(got, torch.from_numpy(golden(name)["net"])) < UNET_TOL[prec]
 
 
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("env", [{"MDT_NO_PACKED_CROSS": "1"}, {"MDT_PACK_SELF": "0"}, {"MDT_PACKED_CROSS_MAXL": "8"},
+                                 {"MDT_NO_FUSED_ATTN": "1"}, {"MDT_SERPENTINE": "0"}])
+def test_unet_eval_with_a_fast_path_switched_off(env, prec, model_cache, monkeypatch):
+    """Every attention mode of the fused kernel stays reachable and correct: cp.async-staged cross-attention and per-sample
+    self-attention at L = 4 (the defaults pack those), the packed cross path limited to the short levels, the unfused
+    projection + streaming attention kernels, and front-to-back traversal."""
+    from moleculediffusiontransformer_b200.plan import SamplerPlan
+
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    name = "inv64_cs7p5"
+    kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES[name]
+    m = model_cache(kind, kw, mseed)
+    seq, noise0, _ = make_inputs(name)
+    plan = SamplerPlan(m, "cuda:0", precision=prec, max_batch=8)
+    try:
+        got = plan.unet_forward(noise0, 0.37, seq, cond_scale=cs).cpu()
+    finally:
+        plan.close()
+    assert orc.rel_l2(got, torch.from_numpy(golden(name)["net"])) < UNET_TOL[prec]
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_sample_fp32_vs_reference_fixture(name, model_cache):
     kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES[name]
