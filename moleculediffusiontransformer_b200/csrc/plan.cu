@@ -584,28 +584,30 @@ struct Builder {
         cl.wkv = upload(wkv); cl.bkv = upload(bkv);
         cl.kv_cond = dalloc((size_t)pl.Bmax * pl.cfg.ctx_max_length * 2 * Hd);
         cl.kv_null = dalloc((size_t)pl.cfg.ctx_max_length * 2 * Hd);
-        if (fast) {
+        const bool fuse_cross = fast && fuse_attn && gemm_attn_supported(pl.prec, C, L, heads, d, 1, pl.cfg.ctx_max_length);
+        // short contexts (<= 16 rows): K / V are read in mma.sync B-fragment order straight from a fragment-ordered tf32 cache and
+        // 16 / L samples share one m16 tile (gemm_attn.cu mode 3); otherwise the kernels read row-major K / V in the operand dtype
+        const char* np = getenv("MDT_NO_PACKED_CROSS");
+        const char* ml = getenv("MDT_PACKED_CROSS_MAXL");
+        const int maxl = ml ? atoi(ml) : 16;
+        const bool packed = fuse_cross && (L == 4 || L == 8 || L == 16) && L <= maxl && pl.cfg.ctx_max_length <= 16 && d == 64 &&
+                            !(np && np[0] != '0');
+        if (packed) {
+          cl.kvf_cond = dalloc((size_t)pl.Bmax * heads * 2048);
+          cl.kvf_null = dalloc((size_t)heads * 2048);
+        } else if (fast) {
           cl.kv_cond_op = dalloc((size_t)pl.Bmax * pl.cfg.ctx_max_length * 2 * Hd);   // sized in floats; bf16 uses half
           cl.kv_null_op = dalloc((size_t)pl.cfg.ctx_max_length * 2 * Hd);
         }
         const int layer = (int)pl.cross.size();
         pl.cross.push_back(cl);
-        const bool fuse_cross = fast && fuse_attn && gemm_attn_supported(pl.prec, C, L, heads, d, 1, pl.cfg.ctx_max_length);
         if (fuse_cross) {
           emit_ln_apply(prog, t, C, L, tn);
-          // the fused kernel streams fp32 K/V with cp.async in both tensor-core modes (tf32: rounded copy, bf16: the fp32 cache)
-          // short query blocks (L = 4, 8) with a context of at most 16 rows: 16 / L samples per m16 tile, K / V from a fragment-ordered cache
-          const char* np = getenv("MDT_NO_PACKED_CROSS");
-          const char* ml = getenv("MDT_PACKED_CROSS_MAXL");
-          const int maxl = ml ? atoi(ml) : 16;
-          if ((L == 4 || L == 8 || L == 16) && L <= maxl && pl.cfg.ctx_max_length <= 16 && d == 64 && !(np && np[0] != '0')) {
-            CrossLayer& clr = pl.cross[layer];
-            clr.kvf_cond = dalloc((size_t)pl.Bmax * heads * 2048);
-            clr.kvf_null = dalloc((size_t)heads * 2048);
-            cl = clr;
-          }
-          emit_gemm_attn(prog, tn, C, L, d_wq, d_bq, 1, layer, pl.prec == MDT_PREC_TF32 ? cl.kv_cond_op : (void*)cl.kv_cond,
-                         pl.prec == MDT_PREC_TF32 ? cl.kv_null_op : (void*)cl.kv_null, cl.kvf_cond, cl.kvf_null);
+          // row-major variant: the fused kernel streams fp32 K/V with cp.async in both tensor-core modes (tf32: rounded copy, bf16: the
+          // fp32 cache); the null-branch pointer doubles as the "has a null branch" flag, so it is passed in the packed variant too
+          const bool op_copy = pl.prec == MDT_PREC_TF32 && !packed;
+          emit_gemm_attn(prog, tn, C, L, d_wq, d_bq, 1, layer, op_copy ? cl.kv_cond_op : (void*)cl.kv_cond,
+                         op_copy ? cl.kv_null_op : (void*)cl.kv_null, cl.kvf_cond, cl.kvf_null);
         } else if (fast) {
           emit_ln_apply(prog, t, C, L, tn);
           emit_gemm_tma(prog, tn, C, L, 1, d_wq, d_bq, Hd, 0, nullptr, nullptr, pl.qc);
