@@ -17,7 +17,9 @@ namespace mdt {
 namespace tc {
 
 constexpr int A_TM = 128;
-constexpr int A_STAGES = 2;
+constexpr int A_STAGES = 2;           // operand ring depth of the modes that need the shared memory for q / k / v staging or K / V scratch
+constexpr int A_STAGES_PACKED = 4;    // mode 3 stages only q: the ring can hold half a level-2 tile
+__host__ __device__ constexpr int attn_stages(int mode) { return mode == 3 ? A_STAGES_PACKED : A_STAGES; }
 constexpr int A_ABYTES = A_TM * 128;
 constexpr int A_EPI_WARPS = 8;
 constexpr int A_THREADS = 64 + 32 * A_EPI_WARPS;
@@ -38,9 +40,10 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
                                                                 const GemmAttnParams p, const uint32_t idesc) {
   constexpr int KCH = (KIND == 1) ? 32 : 64;
   constexpr bool CROSS = MODE >= 2;
+  constexpr int NST = attn_stages(MODE);
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B operand tiles need 1024-byte alignment
-  __shared__ __align__(8) uint64_t full_bar[A_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[A_STAGES];
+  __shared__ __align__(8) uint64_t full_bar[NST];
+  __shared__ __align__(8) uint64_t empty_bar[NST];
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_s;
@@ -55,12 +58,12 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
   const int m_tiles = (p.M + A_TM - 1) / A_TM;
   const int total_tiles = m_tiles * p.heads;
   const uint32_t tmem_cols = CROSS ? 128u : 512u;   // two accumulators of BN columns
-  float* Qs = reinterpret_cast<float*>(smem + A_STAGES * stage_bytes);
+  float* Qs = reinterpret_cast<float*>(smem + NST * stage_bytes);
   float* Ks = Qs + A_TM * A_LD;                       // self: staged k rows; cross: per-warp K scratch base
   float* Vs = Ks + A_TM * A_LD;
 
   if (tid == 0) {
-    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], A_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -80,8 +83,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
         const int te = p.rev ? total_tiles - 1 - t : t;
         const int mt = te / p.heads, h = te - mt * p.heads;
         for (int kc = 0; kc < p.kchunks; ++kc, ++c) {
-          const int stage = c % A_STAGES;
-          const uint32_t phase = (uint32_t)(c / A_STAGES) & 1u;
+          const int stage = c % NST;
+          const uint32_t phase = (uint32_t)(c / NST) & 1u;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * stage_bytes;
           mbar_arrive_expect_tx(&full_bar[stage], tx);
@@ -100,8 +103,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
       for (int k0 = 0; k0 < p.kchunks; ++k0, ++c) {
-        const int stage = c % A_STAGES;
-        const uint32_t phase = (uint32_t)(c / A_STAGES) & 1u;
+        const int stage = c % NST;
+        const uint32_t phase = (uint32_t)(c / NST) & 1u;
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
@@ -291,7 +294,7 @@ static size_t gemm_attn_smem(const GemmAttnParams& p, int nk_max) {
   if (p.cross && p.kvf_c) {}                                                       // packed path: K / V fragments come from global
   else if (p.cross) stg += (size_t)tc::A_EPI_WARPS * 2 * 2 * nk_max * tc::A_LD * 4;   // per warp: two [K | V] scratch buffers
   else stg += 2 * (size_t)tc::A_TM * tc::A_LD * 4;
-  return tc::A_STAGES * stage + stg + 1024;
+  return tc::attn_stages((p.cross && p.kvf_c) ? 3 : 0) * stage + stg + 1024;
 }
 
 bool gemm_attn_supported(int kind, int C, int L, int heads, int d, int cross, int nk_max) {
