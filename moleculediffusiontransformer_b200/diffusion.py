@@ -14,9 +14,8 @@ The scalar plan reproduces the reference's float32-tensor / Python-double mixing
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
 from math import sqrt
-from typing import List, Optional
+from typing import List
 
 import numpy as np
 import torch

@@ -18,8 +18,8 @@ Key layout / construction order follow the reference modules:
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field, asdict
-from typing import List, Optional, Sequence
+from dataclasses import asdict, dataclass
+from typing import Optional, Sequence
 
 import torch
 import torch.nn as nn

@@ -1,5 +1,4 @@
 """Parity of the CUDA path (through the public API / C ABI) against the reference fixtures and the CPU oracle."""
-import numpy as np
 import pytest
 import torch
 
