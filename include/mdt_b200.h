@@ -126,7 +126,10 @@ int64_t mdt_plan_launch_count(const mdt_plan* plan);
  *   out_dev         [B, P, L] fp32       result (reference layout), may be NULL if tokens_dev given
  *   tokens_dev      [B, L] uint8         argmax over P (generative.py:1212-1213), may be NULL
  *   stream          cudaStream_t as void* (NULL = legacy default stream)
- * B may exceed cfg->max_batch: the plan walks it in chunks.  Asynchronous on `stream`. */
+ * B may exceed cfg->max_batch: the plan walks it in chunks.  Asynchronous on `stream`.
+ * Rows whose midpoint is the start (sigma_mid == sigma, dt_mid == 0, the `_b` coefficients those of sigma) describe first-order
+ * ancestral Euler steps (AEulerSampler, diffusion.py:456-483): when every row is of that kind the first denoiser call of each
+ * iteration is skipped (one call per step). */
 int mdt_plan_sample(mdt_plan* plan, const float* cond_dev, int32_t n_ctx, const float* noise0_dev,
                     const float* step_noise_dev, const mdt_iter_scalars* iters, int32_t n_iters,
                     uint64_t seed, uint64_t sample_offset, int64_t B, float cond_scale, int32_t clamp,

@@ -1260,7 +1260,20 @@ int mdt_plan_unet_forward(mdt_plan* pl, const float* x_dev, float time, const fl
   return 0;
 }
 
-static void run_iteration(mdt_plan& pl, StepParams& sp, int Beff, int Bc, int n_ctx, cudaStream_t s) {
+// single_call: every row of the scalar table has its midpoint at the start (sigma_mid == sigma, dt_mid == 0), i.e. a first-order
+// ancestral Euler step (AEulerSampler, diffusion.py:456-483).  Call A would evaluate the denoiser at (x, sigma) only to move by
+// dt_mid = 0, so it is skipped: update B runs on (x, sigma) directly (x_mid aliases x) and the call counter still advances by two
+// (the time tables keep one slot pair per iteration).
+static void run_iteration(mdt_plan& pl, StepParams& sp, int Beff, int Bc, int n_ctx, bool single_call, cudaStream_t s) {
+  if (single_call) {
+    StepParams sb = sp;
+    sb.xmid = sp.x;
+    run_program(pl, pl.unet, Beff, Bc, n_ctx, s);
+    CK(launch_step_update(1, sb, s));
+    CK(launch_add_int(pl.d_call, 2, s));
+    pl.launches += 2;
+    return;
+  }
   run_program(pl, pl.unet, Beff, Bc, n_ctx, s);
   CK(launch_step_update(0, sp, s));
   CK(launch_add_int(pl.d_call, 1, s));
@@ -1294,6 +1307,8 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
     CK(cudaStreamSynchronize(s));
     memcpy(pl->h_iters, iters, sizeof(IterScalars) * n_iters);
     for (int i = 0; i < n_iters; ++i) { pl->h_tcalls[2 * i] = iters[i].c_noise_a; pl->h_tcalls[2 * i + 1] = iters[i].c_noise_b; }
+    bool single_call = true;   // first-order rows (see run_iteration)
+    for (int i = 0; i < n_iters; ++i) single_call = single_call && iters[i].dt_mid == 0.0f && iters[i].sigma_mid == iters[i].sigma;
     CK(cudaMemcpyAsync(pl->d_iters, pl->h_iters, sizeof(IterScalars) * n_iters, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(pl->t_calls, pl->h_tcalls, sizeof(float) * 2 * n_iters, cudaMemcpyHostToDevice, s));
     run_time_tables(*pl, 2 * n_iters, s);
@@ -1316,7 +1331,7 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
       if (pl->use_graph && !pl->taps_on) {
         // one captured iteration, replayed n_iters times; all per-iteration data is device resident
         std::vector<long long> key = {Bc, n_ctx, cfg ? 1 : 0, (long long)(uintptr_t)sp.noise, sp.noise_iter_stride,
-                                      (long long)n_iters, (long long)(cond_scale * 65536.0)};
+                                      (long long)n_iters, (long long)(cond_scale * 65536.0), single_call ? 1 : 0};
         auto it = pl->graphs.find(key);
         if (it == pl->graphs.end()) {
           if (pl->graphs.size() > 16) { for (auto& kv : pl->graphs) cudaGraphExecDestroy(kv.second.exec); pl->graphs.clear(); }
@@ -1325,7 +1340,7 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
           cudaGraph_t graph = nullptr;
           const long long before = pl->launches;
           CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-          try { run_iteration(*pl, sp, Beff, Bc, n_ctx, cs); }
+          try { run_iteration(*pl, sp, Beff, Bc, n_ctx, single_call, cs); }
           catch (...) { cudaStreamEndCapture(cs, &graph); if (graph) cudaGraphDestroy(graph); cudaStreamDestroy(cs); throw; }
           CK(cudaStreamEndCapture(cs, &graph));
           pl->launches = before;
@@ -1338,9 +1353,9 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
         long long per_iter = 0;
         for (const Op& op : pl->unet) { (void)op; per_iter++; }
         for (int i = 0; i < n_iters; ++i) CK(cudaGraphLaunch(it->second.exec, s));
-        pl->launches += (long long)n_iters * (2 * per_iter + 4);
+        pl->launches += (long long)n_iters * (single_call ? per_iter + 2 : 2 * per_iter + 4);
       } else {
-        for (int i = 0; i < n_iters; ++i) run_iteration(*pl, sp, Beff, Bc, n_ctx, s);
+        for (int i = 0; i < n_iters; ++i) run_iteration(*pl, sp, Beff, Bc, n_ctx, single_call, s);
       }
       CK(launch_finalize(pl->x, out_dev ? out_dev + (size_t)b0 * per : nullptr,
                          tokens_dev ? tokens_dev + (size_t)b0 * L : nullptr, Bc, P, L, clamp, s));
@@ -1399,7 +1414,7 @@ int mdt_plan_inpaint(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const f
           CK(launch_set_int(pl->d_call, 2 * i, s));
           const long long d_step = d++;
           sp.noise = nz(d_step); sp.noise_stream = (int)d_step;
-          run_iteration(*pl, sp, Beff, Bc, n_ctx, s);
+          run_iteration(*pl, sp, Beff, Bc, n_ctx, false, s);
           pl->launches += 2;
           if (r < R - 1) {
             const long long d_re = d++;

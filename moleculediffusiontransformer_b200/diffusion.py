@@ -53,6 +53,20 @@ class ADPM2Sampler:
         return sigma_up, sigma_down, sigma_mid
 
 
+class AEulerSampler:
+    """Ancestral Euler sampler description (diffusion.py:456-483): one denoiser call per step.
+
+    On the device it is the second half of an ADPM2 iteration whose midpoint coincides with the start: the scalar table
+    carries ``sigma_mid = sigma`` and ``dt_mid = 0`` and the C side skips the first denoiser call for such rows."""
+
+    diffusion_aliases = ("k", "vk")
+
+    def get_sigmas(self, sigma: torch.Tensor, sigma_next: torch.Tensor):
+        sigma_up = sqrt(sigma_next ** 2 * (sigma ** 2 - sigma_next ** 2) / sigma ** 2)
+        sigma_down = sqrt(sigma_next ** 2 - sigma_up ** 2)
+        return sigma_up, sigma_down
+
+
 # One row per denoiser call / per ADPM2 iteration.  Layout shared with include/mdt_b200.h
 # (struct mdt_iter_scalars): 2 x {c_in, c_noise, c_skip, c_out, inv-free sigma divisor} + update coefficients.
 ITER_SCALAR_FIELDS = (
@@ -73,13 +87,17 @@ def _scale_weights(sigma: torch.Tensor, sigma_data: float):
     return float(c_in), float(c_noise), float(c_skip), float(c_out)
 
 
-def build_iter_scalars(sigmas: torch.Tensor, num_steps: int, sampler: ADPM2Sampler, sigma_data: float) -> np.ndarray:
+def build_iter_scalars(sigmas: torch.Tensor, num_steps: int, sampler, sigma_data: float) -> np.ndarray:
     """Host plan: float32 table [num_steps-1, 13] of every scalar the fused step kernels need."""
     sigmas = sigmas.detach().to("cpu", torch.float32)
     rows: List[List[float]] = []
     for i in range(num_steps - 1):
         sig, sig_next = sigmas[i], sigmas[i + 1]
-        sigma_up, sigma_down, sigma_mid = sampler.get_sigmas(sig, sig_next)
+        if isinstance(sampler, AEulerSampler):
+            sigma_up, sigma_down = sampler.get_sigmas(sig, sig_next)
+            sigma_mid = sig                        # degenerate midpoint: the device runs the (x, sigma) evaluation only
+        else:
+            sigma_up, sigma_down, sigma_mid = sampler.get_sigmas(sig, sig_next)
         sigma_mid = torch.as_tensor(sigma_mid, dtype=torch.float32)
         a = _scale_weights(sig, sigma_data)
         b = _scale_weights(sigma_mid, sigma_data)

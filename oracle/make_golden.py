@@ -59,8 +59,35 @@ def main_inpaint():
         print(f"{name}: out.sum={out.double().sum():.6f} draws={st['i']}")
 
 
+AEULER_CASES = ("inv64_cs7p5", "inv64_short_ctx_clamp")
+
+
+def main_aeuler():
+    """The reference's own injection point: model.diffusion.sample(noise, sampler=AEulerSampler(), ...) with the
+    conditioning embedding built exactly as QMDiffusion.sample builds it (generative.py:838-850) and every randn_like injected."""
+    rl.load()
+    import MoleculeDiffusion.diffusion as rd
+
+    for name in AEULER_CASES:
+        kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES[name]
+        m = rl.build_model(kind, seed=mseed, **kw)
+        seq, noise0, step_noise = make_inputs(name)
+        with torch.no_grad():
+            x = seq.float().unsqueeze(2)
+            emb = m.GELUact(m.fc1(x))
+            emb = torch.cat((emb, m.p_enc_1d(emb)), 2)
+        with rl.injected_noise(noise0, step_noise) as st:
+            out = m.diffusion.sample(noise0, embedding=emb, embedding_scale=cs, num_steps=steps, sampler=rd.AEulerSampler(),
+                                     sigma_schedule=rd.KarrasSchedule(sigma_min=0.001, sigma_max=9.0, rho=3.0), clamp=clamp)
+        assert st["i"] == steps - 1, (st["i"], steps)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"aeuler_{name}.npz"), out=out.numpy())
+        print(f"aeuler_{name}: out.sum={out.double().sum():.6f} draws={st['i']}")
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["inpaint"]:
         main_inpaint()
+    elif sys.argv[1:] == ["aeuler"]:
+        main_aeuler()
     else:
         main(sys.argv[1:] or None)

@@ -243,6 +243,19 @@ def adpm2_sample(fn: Callable, noise: Tensor, sigmas: Tensor, num_steps: int, st
     return x
 
 
+def aeuler_sample(fn: Callable, noise: Tensor, sigmas: Tensor, num_steps: int, step_noise) -> Tensor:
+    """AEulerSampler.forward/step/get_sigmas (diffusion.py:456-483); ``step_noise[i]`` replaces randn_like."""
+    x = sigmas[0] * noise
+    for i in range(num_steps - 1):
+        sigma, sigma_next = sigmas[i], sigmas[i + 1]
+        sigma_up = math.sqrt(sigma_next ** 2 * (sigma ** 2 - sigma_next ** 2) / sigma ** 2)
+        sigma_down = math.sqrt(sigma_next ** 2 - sigma_up ** 2)
+        d = (x - fn(x, sigma)) / sigma
+        x_next = x + d * (sigma_down - sigma)
+        x = x_next + step_noise[i] * sigma_up
+    return x
+
+
 def adpm2_inpaint(fn: Callable, source: Tensor, mask: Tensor, sigmas: Tensor, num_steps: int, num_resamples: int, draws,
                   rho: float = 1.0) -> Tensor:
     """ADPM2Sampler.inpaint (diffusion.py:526-549); ``draws`` replays every randn_like in call order."""
@@ -279,12 +292,18 @@ def inpaint(sd: SD, cfg: dict, sequences: Tensor, source: Tensor, mask: Tensor, 
 
 @torch.no_grad()
 def sample(sd: SD, cfg: dict, sequences: Tensor, noise0: Tensor, step_noise, cond_scale: float, timesteps: int,
-           clamp: bool = False, pos_emb_fourier: bool = True, pos_emb_fourier_add: bool = False) -> Tensor:
-    """QMDiffusion.sample / QMDiffusionForward.sample (generative.py:834-870, 146-180) with injected noise."""
+           clamp: bool = False, pos_emb_fourier: bool = True, pos_emb_fourier_add: bool = False, sampler: str = "adpm2") -> Tensor:
+    """QMDiffusion.sample / QMDiffusionForward.sample (generative.py:834-870, 146-180) with injected noise; ``sampler="aeuler"``
+    restates ``model.diffusion.sample(..., sampler=AEulerSampler())`` (diffusion.py:724-741, 456-483)."""
     emb = encode_conditioning(sd, sequences, pos_emb_fourier, pos_emb_fourier_add)
     sigmas = karras_sigmas(timesteps)
     fn = lambda x, sigma: denoise(sd, cfg, x, sigma, emb, cond_scale)
-    x = adpm2_sample(fn, noise0, sigmas, timesteps, step_noise)
+    if sampler == "adpm2":
+        x = adpm2_sample(fn, noise0, sigmas, timesteps, step_noise)
+    elif sampler == "aeuler":
+        x = aeuler_sample(fn, noise0, sigmas, timesteps, step_noise)
+    else:
+        raise ValueError(sampler)
     return x.clamp(-1.0, 1.0) if clamp else x
 
 

@@ -186,6 +186,30 @@ def test_stale_rows_of_a_poisoned_workspace_never_leak(prec, umma, model_cache, 
     assert torch.equal(again, fresh)
 
 
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("tf32", 1e-3)])
+@pytest.mark.parametrize("name", ["inv64_cs7p5", "inv64_short_ctx_clamp"])
+def test_aeuler_sampler_through_the_reference_injection_point(name, prec, tol, model_cache):
+    """``model.diffusion.sample(noise, sampler=<Sampler>, sigma_schedule=<Schedule>, ...)``.  AEulerSampler
+    (diffusion.py:456-483) runs as one denoiser call per step on the same executor; fixtures from the reference itself."""
+    import moleculediffusiontransformer_b200 as mdt
+
+    kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES[name]
+    m = model_cache(kind, kw, mseed)
+    seq, noise0, step_noise = make_inputs(name)
+    plan = m._plan_for(torch.device("cuda:0"), prec, batch=b, timesteps=steps)
+    before = plan.launch_count
+    got = m.diffusion.sample(noise0.to("cuda:0"), num_steps=steps, sampler=mdt.AEulerSampler(),
+                             sigma_schedule=mdt.KarrasSchedule(sigma_min=0.001, sigma_max=9.0, rho=3.0), clamp=clamp,
+                             sequences=seq, embedding_scale=cs, step_noise=step_noise, precision=prec).cpu()
+    ae_launches = plan.launch_count - before
+    ref = torch.from_numpy(golden("aeuler_" + name)["out"])
+    assert orc.rel_l2(got, ref) < tol
+    assert (_tokens(got) == _tokens(ref)).float().mean() >= 0.999
+    before = plan.launch_count
+    m.sample(seq, "cuda:0", cond_scale=cs, timesteps=steps, clamp=clamp, noise=noise0, step_noise=step_noise, precision=prec)
+    assert ae_launches < 0.62 * (plan.launch_count - before)            # one denoiser call per step instead of two
+
+
 def test_philox_noise_is_sharding_invariant_and_deterministic(model_cache):
     from moleculediffusiontransformer_b200 import ADPM2Sampler, KarrasSchedule
     from moleculediffusiontransformer_b200.plan import SamplerPlan

@@ -71,6 +71,21 @@ def test_iter_scalars_match_reference_arithmetic():
             assert tab[i, 1] == np.float32((sigmas ** 2 + 0.1 ** 2) ** -0.5)
 
 
+def test_aeuler_rows_are_degenerate_adpm2_rows():
+    """AEulerSampler rows: midpoint at the start (what the C side recognises as one denoiser call per step), same sigma_up /
+    sigma_down as ADPM2 (diffusion.py:467-469 vs 495-498)."""
+    from moleculediffusiontransformer_b200 import ADPM2Sampler, AEulerSampler, KarrasSchedule, build_iter_scalars
+
+    sig = KarrasSchedule(0.001, 9.0, 3.0)(16)
+    ae = build_iter_scalars(sig, 16, AEulerSampler(), 0.1)
+    ad = build_iter_scalars(sig, 16, ADPM2Sampler(1.0), 0.1)
+    assert ae.shape == ad.shape == (15, 13)
+    assert np.array_equal(ae[:, 5], ae[:, 0]) and np.all(ae[:, 10] == 0.0)                  # sigma_mid == sigma, dt_mid == 0
+    assert np.array_equal(ae[:, 6:10], ae[:, 1:5])                                          # call-B coefficients are sigma's
+    assert np.array_equal(ae[:, [0, 1, 2, 3, 4, 11, 12]], ad[:, [0, 1, 2, 3, 4, 11, 12]])   # sigma, call-A coefficients, dt_down, sigma_up
+    assert np.all(ad[:, 10] < 0.0)                                                          # an ADPM2 row can never look first order
+
+
 def test_c_scalar_helpers_match_python():
     from moleculediffusiontransformer_b200 import ADPM2Sampler, KarrasSchedule, _capi, build_iter_scalars
 

@@ -76,3 +76,18 @@ def test_inpaint_matches_reference(name, model_cache):
     ref = torch.from_numpy(golden(name)["out"])
     assert orc.rel_l2(out, ref) < 1e-5
     assert torch.equal(out[:, :, :keep], source[:, :, :keep])          # kept region is the draft, bit for bit
+
+
+@pytest.mark.parametrize("name", ["inv64_cs7p5", "inv64_short_ctx_clamp"])
+def test_aeuler_sampler_matches_reference(name, model_cache):
+    """Oracle restatement of AEulerSampler (diffusion.py:456-483) against fixtures produced by the reference through its own
+    injection point ``model.diffusion.sample(noise, sampler=AEulerSampler(), ...)`` (oracle/make_golden.py aeuler)."""
+    kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES[name]
+    m = model_cache(kind, kw, mseed)
+    sd, cfg = _sd_cfg(m)
+    seq, noise0, step_noise = make_inputs(name)
+    out = orc.sample(sd, cfg, seq, noise0, step_noise, cs, steps, clamp, sampler="aeuler")
+    ref = torch.from_numpy(golden("aeuler_" + name)["out"])
+    assert orc.rel_l2(out, ref) < 1e-5
+    assert (orc.tokens_from_logits(out) == orc.tokens_from_logits(ref)).float().mean() == 1.0
+    assert orc.rel_l2(out, torch.from_numpy(golden(name)["out"])) > 1e-2        # and it is not the ADPM2 result
