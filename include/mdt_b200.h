@@ -104,6 +104,10 @@ int mdt_device_count(void);
  * in C for non-Python hosts.  rho is the sampler's rho (1.0 for the QM wrappers). */
 int mdt_adpm2_scalars(const float* sigmas, int n_iters, double rho, double sigma_data, mdt_iter_scalars* out);
 
+/* Same for AEulerSampler.get_sigmas / step (diffusion.py:467-475): rows with sigma_mid = sigma and dt_mid = 0, which
+ * mdt_plan_sample executes as one denoiser call per step. */
+int mdt_aeuler_scalars(const float* sigmas, int n_iters, double sigma_data, mdt_iter_scalars* out);
+
 /* KarrasSchedule.forward (diffusion.py:333-342): out[num_steps + 1], last entry 0. */
 int mdt_karras_sigmas(int num_steps, double sigma_min, double sigma_max, double rho, float* out);
 

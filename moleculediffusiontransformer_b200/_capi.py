@@ -11,7 +11,7 @@ MDT_MAX_LEVELS = 4
 PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
 
 EXPORTS = [
-    "mdt_last_error", "mdt_abi_version", "mdt_device_count", "mdt_adpm2_scalars", "mdt_karras_sigmas",
+    "mdt_last_error", "mdt_abi_version", "mdt_device_count", "mdt_adpm2_scalars", "mdt_aeuler_scalars", "mdt_karras_sigmas",
     "mdt_plan_create", "mdt_plan_destroy", "mdt_plan_device_bytes", "mdt_plan_launch_count", "mdt_plan_sample",
     "mdt_plan_inpaint", "mdt_plan_unet_forward", "mdt_plan_enable_taps", "mdt_plan_read_tap", "mdt_op_linear", "mdt_op_step_update",
     "mdt_op_decode_tokens",
@@ -67,6 +67,7 @@ def load() -> C.CDLL:
     lib.mdt_abi_version.restype = C.c_int
     lib.mdt_device_count.restype = C.c_int
     lib.mdt_adpm2_scalars.argtypes = [vp, C.c_int, f64, f64, C.POINTER(MdtIterScalars)]
+    lib.mdt_aeuler_scalars.argtypes = [vp, C.c_int, f64, C.POINTER(MdtIterScalars)]
     lib.mdt_karras_sigmas.argtypes = [C.c_int, f64, f64, f64, vp]
     lib.mdt_plan_create.argtypes = [C.POINTER(MdtConfig), C.POINTER(MdtTensor), i64, C.c_int, C.POINTER(vp)]
     lib.mdt_plan_destroy.argtypes = [vp]

@@ -1130,6 +1130,24 @@ int mdt_adpm2_scalars(const float* sigmas, int n_iters, double rho, double sigma
   return 0;
 }
 
+int mdt_aeuler_scalars(const float* sigmas, int n_iters, double sigma_data, mdt_iter_scalars* out) {
+  if (!sigmas || !out || n_iters < 0) return fail(MDT_ERR_INVALID, "bad arguments");
+  for (int i = 0; i < n_iters; ++i) {
+    const float s = sigmas[i], sn = sigmas[i + 1];
+    const float sn2 = sn * sn, s2 = s * s;
+    const double up = sqrt((double)(sn2 * (s2 - sn2) / s2));
+    const double down = sqrt((double)(sn2 - (float)(up * up)));
+    mdt_iter_scalars& o = out[i];
+    o.sigma = s; o.sigma_mid = s;      // midpoint at the start: mdt_plan_sample runs one denoiser call per step for such rows
+    scale_weights(s, sigma_data, &o.c_in_a, &o.c_noise_a, &o.c_skip_a, &o.c_out_a);
+    o.c_in_b = o.c_in_a; o.c_noise_b = o.c_noise_a; o.c_skip_b = o.c_skip_a; o.c_out_b = o.c_out_a;
+    o.dt_mid = 0.0f;
+    o.dt_down = (float)down - s;
+    o.sigma_up = (float)up;
+  }
+  return 0;
+}
+
 int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_tensors, int device, mdt_plan** out) {
   if (!cfg || !tensors || !out) return fail(MDT_ERR_INVALID, "null argument");
   if (cfg->abi_version != MDT_ABI_VERSION) return fail(MDT_ERR_INVALID, "ABI version mismatch (%d != %d)", cfg->abi_version, MDT_ABI_VERSION);

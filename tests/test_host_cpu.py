@@ -101,6 +101,13 @@ def test_c_scalar_helpers_match_python():
         _capi.check(lib.mdt_adpm2_scalars(s32.ctypes.data, n - 1, 1.0, 0.1, arr))
         ct = np.ctypeslib.as_array(ctypes.cast(arr, ctypes.POINTER(ctypes.c_float)), shape=(n - 1, 13))
         assert np.allclose(ct, tab, rtol=5e-7, atol=0)
+        from moleculediffusiontransformer_b200 import AEulerSampler
+        tab_e = build_iter_scalars(sig, n, AEulerSampler(), 0.1)
+        arr_e = (_capi.MdtIterScalars * (n - 1))()
+        _capi.check(lib.mdt_aeuler_scalars(s32.ctypes.data, n - 1, 0.1, arr_e))
+        ce = np.ctypeslib.as_array(ctypes.cast(arr_e, ctypes.POINTER(ctypes.c_float)), shape=(n - 1, 13))
+        assert np.allclose(ce, tab_e, rtol=5e-7, atol=0)
+        assert np.array_equal(ce[:, 5], ce[:, 0]) and np.all(ce[:, 10] == 0.0)      # exactly the rows the driver recognises
     assert lib.mdt_karras_sigmas(1, 0.001, 9.0, 3.0, c.ctypes.data) < 0
     assert b"num_steps" in lib.mdt_last_error()
 
