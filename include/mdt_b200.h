@@ -139,6 +139,11 @@ int mdt_plan_sample(mdt_plan* plan, const float* cond_dev, int32_t n_ctx, const 
                     uint64_t seed, uint64_t sample_offset, int64_t B, float cond_scale, int32_t clamp,
                     float* out_dev, uint8_t* tokens_dev, void* stream);
 
+/* Context mode: pre_encoded != 0 makes `cond_dev` of the sampling entry points the already encoded conditioning embedding
+ * [B, n_ctx, ctx_features] fp32 -- what QMDiffusion.sample hands to XDiffusion_x.sample as `embedding=` (generative.py:838-860,
+ * diffusion.py:724-741) -- instead of the raw `sequences` [B, n_ctx]; the device-side encoder is skipped.  Default 0. */
+int mdt_plan_set_context_mode(mdt_plan* plan, int pre_encoded);
+
 /* Inpainting: replaces QMDiffusion.inpaint -> XDiffusion_x.inpaint -> DiffusionInpainter.forward ->
  * ADPM2Sampler.inpaint (generative.py:871-914, diffusion.py:744-767, 612-625, 526-549).
  *   source_dev [B, P, L] fp32   the draft to keep where mask != 0;   mask_dev [B, P, L] uint8

@@ -328,12 +328,16 @@ __global__ void attention_kernel(const AttnParams p, int warps_per_cta) {
 }
 
 cudaError_t init_prep();
+static cudaError_t init_step_kernels();
+// dynamic shared memory the sampler-state kernels may request for their (P, L) transposition tile (opt-in above 48 KB)
+#define MDT_STEP_SMEM_MAX ((size_t)200 * 1024)
 cudaError_t init_kernels() {
   cudaError_t e = cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = init_prep();
   if (e == cudaSuccess) e = init_attention_bulk();
+  if (e == cudaSuccess) e = init_step_kernels();
   return e;
 }
 
@@ -639,6 +643,7 @@ cudaError_t launch_step_init(const float* noise0, float* x, float* xin, const It
   if (B <= 0) return cudaSuccess;
   if ((P * L) % 4) return cudaErrorInvalidValue;
   const size_t smem = noise0 ? (size_t)P * (L + 1) * sizeof(float) : 0;
+  if (smem > MDT_STEP_SMEM_MAX) return cudaErrorInvalidValue;
   step_init_kernel<<<B, 256, smem, s>>>(noise0, x, xin, iters, seed, sample_offset, B, P, L, cfg);
   return cudaGetLastError();
 }
@@ -656,8 +661,11 @@ __global__ void step_update_kernel(const StepParams p) {
   const IterScalars it = p.iters[iter];
   const bool last = (iter == p.n_iters - 1);
   const size_t half = (size_t)p.B * n;
-  if (WHICH == 1 && p.noise) {
-    const float* nz = p.noise + (size_t)iter * p.noise_iter_stride + (size_t)b * n;
+  const float* noise = p.run ? p.run->noise : p.noise;
+  const long long noise_stride = p.run ? p.run->noise_iter_stride : p.noise_iter_stride;
+  const float cond_scale = p.run ? p.run->cond_scale : p.cond_scale;
+  if (WHICH == 1 && noise) {
+    const float* nz = noise + (size_t)iter * noise_stride + (size_t)b * n;
     for (int e = threadIdx.x; e < n; e += blockDim.x) { const int pp = e / L, l = e - pp * L; tile[pp * (L + 1) + l] = nz[e]; }
     __syncthreads();
   }
@@ -674,7 +682,7 @@ __global__ void step_update_kernel(const StepParams p) {
       const float4 nn = *reinterpret_cast<const float4*>(p.net + half + o);
       const float un[4] = {nn.x, nn.y, nn.z, nn.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) pred[j] = un[j] + (pred[j] - un[j]) * p.cond_scale;
+      for (int j = 0; j < 4; ++j) pred[j] = un[j] + (pred[j] - un[j]) * cond_scale;
     }
     const float4 xv4 = *reinterpret_cast<const float4*>(p.x + o);
     const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
@@ -684,11 +692,11 @@ __global__ void step_update_kernel(const StepParams p) {
     float res[4];
     float nz[4] = {0.f, 0.f, 0.f, 0.f};
     if (WHICH == 1) {
-      if (p.noise) {
+      if (noise) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const int e = g * 4 + j; const int l = e / P, pp = e - l * P; nz[j] = tile[pp * (L + 1) + l]; }
       } else {
-        const unsigned long long sd = p.rng ? p.rng[0] : p.seed, so = p.rng ? p.rng[1] : p.sample_offset;
+        const unsigned long long sd = p.run ? p.run->seed : p.seed, so = p.run ? p.run->sample_offset : p.sample_offset;
         const float4 z = philox_normal4(sd, so + b, p.noise_stream >= 0 ? (unsigned)p.noise_stream : (unsigned)(iter + 1), (unsigned)g);
         nz[0] = z.x; nz[1] = z.y; nz[2] = z.z; nz[3] = z.w;
       }
@@ -717,15 +725,17 @@ cudaError_t launch_step_update(int which, const StepParams& p, cudaStream_t s) {
   if ((p.P * p.L) % 4) return cudaErrorInvalidValue;
   if (which == 0) step_update_kernel<0><<<p.B, 256, 0, s>>>(p);
   else {
-    const size_t smem = p.noise ? (size_t)p.P * (p.L + 1) * sizeof(float) : 0;
+    const bool tile = p.run ? p.has_noise != 0 : p.noise != nullptr;
+    const size_t smem = tile ? (size_t)p.P * (p.L + 1) * sizeof(float) : 0;
+    if (smem > MDT_STEP_SMEM_MAX) return cudaErrorInvalidValue;
     step_update_kernel<1><<<p.B, 256, smem, s>>>(p);
   }
   return cudaGetLastError();
 }
 
-__global__ void set_u64x2_kernel(unsigned long long* dst, unsigned long long a, unsigned long long b) { dst[0] = a; dst[1] = b; }
-cudaError_t launch_set_u64x2(unsigned long long* dst, unsigned long long a, unsigned long long b, cudaStream_t s) {
-  set_u64x2_kernel<<<1, 1, 0, s>>>(dst, a, b);
+__global__ void set_run_params_kernel(RunParams* dst, const RunParams v) { *dst = v; }
+cudaError_t launch_set_run_params(RunParams* dst, const RunParams& v, cudaStream_t s) {
+  set_run_params_kernel<<<1, 1, 0, s>>>(dst, v);
   return cudaGetLastError();
 }
 __global__ void set_int_kernel(int* dst, int v) { *dst = v; }
@@ -813,8 +823,16 @@ __global__ void finalize_kernel(const float* __restrict__ x, float* __restrict__
 cudaError_t launch_finalize(const float* x, float* out, unsigned char* tokens, int B, int P, int L, int clamp,
                             cudaStream_t s) {
   if (B <= 0) return cudaSuccess;
+  if ((size_t)L * (P + 1) * sizeof(float) > MDT_STEP_SMEM_MAX) return cudaErrorInvalidValue;
   finalize_kernel<<<B, 256, (size_t)L * (P + 1) * sizeof(float), s>>>(x, out, tokens, P, L, clamp);
   return cudaGetLastError();
+}
+
+static cudaError_t init_step_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(step_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MDT_STEP_SMEM_MAX);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(step_update_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MDT_STEP_SMEM_MAX);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MDT_STEP_SMEM_MAX);
+  return e;
 }
 
 // ---- inpainting (ADPM2Sampler.inpaint, diffusion.py:526-549) -----------------------------------------------------------

@@ -79,6 +79,16 @@ struct IterScalars {
   float dt_mid, dt_down, sigma_up;
 };
 
+// Per-run values the captured step kernels read from device memory, so one CUDA graph serves every seed, shard offset,
+// guidance scale and injected-noise buffer (nothing run-specific is baked into the captured kernel arguments).
+struct RunParams {
+  unsigned long long seed, sample_offset;
+  const float* noise;            // injected ancestral noise base for the running chunk, or null => Philox
+  long long noise_iter_stride;   // floats between iterations in the injected noise tensor
+  float cond_scale;
+  int pad;
+};
+
 struct StepParams {
   const IterScalars* iters;  // device table [n_iters]
   const int* call_idx;       // device scalar; iteration = call_idx / 2
@@ -89,7 +99,8 @@ struct StepParams {
   const float* noise;        // injected ancestral noise (B,P,L) for this iteration, or null => Philox
   long long noise_iter_stride;  // floats between iterations in the injected noise tensor
   unsigned long long seed, sample_offset;
-  const unsigned long long* rng;  // optional device pair {seed, sample_offset} overriding the two fields above (graph replays)
+  const RunParams* run;      // optional device block overriding seed / sample_offset / noise / noise_iter_stride / cond_scale (graph replays)
+  int has_noise;             // with `run`: whether run->noise is set (sizes the transposition tile at launch time)
   float cond_scale;
   int cfg;                   // 1 => two branches
   int B, P, L;
@@ -136,7 +147,7 @@ cudaError_t launch_finalize(const float* x, float* out, unsigned char* tokens, i
 cudaError_t launch_inpaint(int mode, float* x, float* xin, const float* source, const unsigned char* mask, const float* noise,
                            float sigma, float c_in, unsigned long long seed, unsigned long long sample_offset, int stream, int B,
                            int P, int L, int cfg, float* out, cudaStream_t s);
-cudaError_t launch_set_u64x2(unsigned long long* dst, unsigned long long a, unsigned long long b, cudaStream_t s);
+cudaError_t launch_set_run_params(RunParams* dst, const RunParams& v, cudaStream_t s);
 cudaError_t launch_kv_fragment_pack(const float* kv, void* out, long long B, int nk, int heads, int d, cudaStream_t s);
 cudaError_t launch_decode_tokens(const uint8_t* tokens, const uint8_t* lut, uint8_t* out, int* lengths, long long B, int L, cudaStream_t s);
 cudaError_t launch_set_int(int* dst, int v, cudaStream_t s);

@@ -146,10 +146,12 @@ struct mdt_plan {
   IterScalars* h_iters = nullptr;  // pinned
   float* h_tcalls = nullptr;       // pinned
   int* d_call = nullptr;
-  unsigned long long* d_rng = nullptr;   // {seed, first sample index} of the running chunk, read by the captured step kernels
+  RunParams* d_run = nullptr;      // seed / first sample index / injected-noise base / guidance scale of the running chunk (captured kernels read it)
+  cudaEvent_t staged = nullptr;    // the pinned staging tables of the previous call have been copied to the device
+  bool ctx_pre_encoded = false;    // cond_dev holds the encoded embedding [B, n_ctx, F] (XDiffusion_x.sample(embedding=...))
   int n_ctx_cur = 0;
-  // graph cache: key (Bc, n_ctx, cfg, has_step_noise)
-  struct GraphEntry { cudaGraphExec_t exec; };
+  // graph cache: key (Bc, n_ctx, cfg, has_step_noise, n_iters, single_call); everything else is device resident
+  struct GraphEntry { cudaGraphExec_t exec; long long launches; };
   std::map<std::vector<long long>, GraphEntry> graphs;
   bool use_graph = true;
   // taps
@@ -1040,8 +1042,11 @@ static void run_time_tables(mdt_plan& pl, int rows, cudaStream_t s) {
 static void run_context(mdt_plan& pl, const float* cond_dev, int Bc, int n_ctx, bool cfg, cudaStream_t s) {
   const mdt_config& c = pl.cfg;
   const int F = pl.F, Hd = pl.Hd;
-  CK(launch_encode_cond(cond_dev, pl.w_fc1, pl.b_fc1, pl.inv_freq, pl.emb, Bc, n_ctx, c.text_embed_dim,
-                        c.pos_emb_fourier ? c.embed_dim_position : 0, c.pos_emb_fourier_add, s));
+  if (pl.ctx_pre_encoded)   // the caller hands over the embedding the wrapper would have computed (generative.py:838-850)
+    CK(cudaMemcpyAsync(pl.emb, cond_dev, (size_t)Bc * n_ctx * F * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  else
+    CK(launch_encode_cond(cond_dev, pl.w_fc1, pl.b_fc1, pl.inv_freq, pl.emb, Bc, n_ctx, c.text_embed_dim,
+                          c.pos_emb_fourier ? c.embed_dim_position : 0, c.pos_emb_fourier_add, s));
   NormStatsParams n{}; n.src0 = pl.emb; n.c0 = F; n.scale1 = 1.f; n.L = 1; n.groups = 1; n.eps = 1e-5f; n.stats = pl.emb_stats; n.rows = Bc * n_ctx;
   CK(launch_rownorm_stats(n, s));
   pl.launches += 2;
@@ -1162,6 +1167,8 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
   if (cfg->max_batch < 1) return fail(MDT_ERR_INVALID, "max_batch must be >= 1");
   if (cfg->precision < 0 || cfg->precision > 2) return fail(MDT_ERR_INVALID, "unknown precision %d", cfg->precision);
   mdt_plan* pl = new mdt_plan();
+  int prev_device = -1;
+  cudaGetDevice(&prev_device);   // creation must not change the caller's current device
   try {
     CK(cudaSetDevice(device));
     CK(init_kernels());
@@ -1192,7 +1199,8 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
     CK(cudaMallocHost((void**)&pl->h_tcalls, sizeof(float) * (pl->max_calls + 2)));
     CK(cudaMalloc((void**)&pl->d_call, sizeof(int)));
     CK(cudaMemset(pl->d_call, 0, sizeof(int)));
-    CK(cudaMalloc((void**)&pl->d_rng, 2 * sizeof(unsigned long long)));
+    CK(cudaMalloc((void**)&pl->d_run, sizeof(RunParams)));
+    CK(cudaEventCreateWithFlags(&pl->staged, cudaEventDisableTiming));
     Builder b(*pl);
     b.build();
     pl->tensors.clear();  // host pointers are not retained past creation
@@ -1200,14 +1208,19 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
     int code = e.code;
     snprintf(g_err, sizeof(g_err), "%s", e.msg.c_str());
     mdt_plan_destroy(pl);
+    if (prev_device >= 0) cudaSetDevice(prev_device);
     return code;
   }
+  if (prev_device >= 0) cudaSetDevice(prev_device);
   *out = pl;
   return 0;
 }
 
 void mdt_plan_destroy(mdt_plan* pl) {
   if (!pl) return;
+  int prev_device = -1;
+  cudaGetDevice(&prev_device);
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_device};
   cudaSetDevice(pl->device);
   cudaDeviceSynchronize();
   dump_op_times();
@@ -1218,13 +1231,20 @@ void mdt_plan_destroy(mdt_plan* pl) {
   if (pl->h_iters) cudaFreeHost(pl->h_iters);
   if (pl->h_tcalls) cudaFreeHost(pl->h_tcalls);
   if (pl->d_call) cudaFree(pl->d_call);
-  if (pl->d_rng) cudaFree(pl->d_rng);
+  if (pl->d_run) cudaFree(pl->d_run);
+  if (pl->staged) cudaEventDestroy(pl->staged);
   cudaGetLastError();
   delete pl;
 }
 
 int64_t mdt_plan_device_bytes(const mdt_plan* pl) { return pl ? (int64_t)(pl->wcap + pl->act_bytes) : 0; }
 int64_t mdt_plan_launch_count(const mdt_plan* pl) { return pl ? pl->launches : 0; }
+
+int mdt_plan_set_context_mode(mdt_plan* pl, int pre_encoded) {
+  if (!pl) return fail(MDT_ERR_INVALID, "null plan");
+  pl->ctx_pre_encoded = pre_encoded != 0;
+  return 0;
+}
 
 int mdt_plan_enable_taps(mdt_plan* pl, int enable) {
   if (!pl) return fail(MDT_ERR_INVALID, "null plan");
@@ -1261,9 +1281,10 @@ int mdt_plan_unet_forward(mdt_plan* pl, const float* x_dev, float time, const fl
     CK(cudaSetDevice(pl->device));
     const bool cfg = cond_scale != 1.0f;
     const int Bc = (int)B, Beff = cfg ? 2 * Bc : Bc;
-    CK(cudaStreamSynchronize(s));
+    CK(cudaEventSynchronize(pl->staged));
     pl->h_tcalls[0] = time;
     CK(cudaMemcpyAsync(pl->t_calls, pl->h_tcalls, sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(pl->staged, s));
     CK(launch_set_int(pl->d_call, 0, s));
     run_time_tables(*pl, 1, s);
     run_context(*pl, cond_dev, Bc, n_ctx, cfg, s);
@@ -1321,19 +1342,21 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
     const bool cfg = cond_scale != 1.0f;
     const int P = pl->P, L = pl->L0;
     const size_t per = (size_t)P * L;
-    // a previous call's async copies out of the pinned staging buffers must have drained
-    CK(cudaStreamSynchronize(s));
+    // a previous call's async copies out of the pinned staging buffers must have drained (only those two copies: the
+    // event sits right behind them, so a back-to-back caller does not wait for the previous sample() to finish)
+    CK(cudaEventSynchronize(pl->staged));
     memcpy(pl->h_iters, iters, sizeof(IterScalars) * n_iters);
     for (int i = 0; i < n_iters; ++i) { pl->h_tcalls[2 * i] = iters[i].c_noise_a; pl->h_tcalls[2 * i + 1] = iters[i].c_noise_b; }
     bool single_call = true;   // first-order rows (see run_iteration)
     for (int i = 0; i < n_iters; ++i) single_call = single_call && iters[i].dt_mid == 0.0f && iters[i].sigma_mid == iters[i].sigma;
     CK(cudaMemcpyAsync(pl->d_iters, pl->h_iters, sizeof(IterScalars) * n_iters, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(pl->t_calls, pl->h_tcalls, sizeof(float) * 2 * n_iters, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(pl->staged, s));
     run_time_tables(*pl, 2 * n_iters, s);
     for (int64_t b0 = 0; b0 < B; b0 += pl->Bmax) {
       const int Bc = (int)std::min<int64_t>(pl->Bmax, B - b0);
       const int Beff = cfg ? 2 * Bc : Bc;
-      run_context(*pl, cond_dev + (size_t)b0 * n_ctx, Bc, n_ctx, cfg, s);
+      run_context(*pl, cond_dev + (size_t)b0 * n_ctx * (pl->ctx_pre_encoded ? pl->F : 1), Bc, n_ctx, cfg, s);
       CK(launch_step_init(noise0_dev ? noise0_dev + (size_t)b0 * per : nullptr, pl->x, pl->xin, pl->d_iters, seed,
                           sample_offset + (uint64_t)b0, Bc, P, L, cfg ? 1 : 0, s));
       CK(launch_set_int(pl->d_call, 0, s));
@@ -1343,13 +1366,15 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
       sp.noise = step_noise_dev ? step_noise_dev + (size_t)b0 * per : nullptr;
       sp.noise_iter_stride = (long long)B * (long long)per;
       sp.seed = seed; sp.sample_offset = sample_offset + (uint64_t)b0; sp.cond_scale = cond_scale; sp.cfg = cfg ? 1 : 0;
-      sp.rng = pl->d_rng;   // seed / offset live in device memory so that one captured graph serves every seed and shard
-      CK(launch_set_u64x2(pl->d_rng, seed, sample_offset + (uint64_t)b0, s));
+      // seed / offset / injected-noise base / guidance scale live in device memory: one captured graph serves all of them
+      sp.run = pl->d_run; sp.has_noise = sp.noise ? 1 : 0;
+      RunParams rp{}; rp.seed = seed; rp.sample_offset = sample_offset + (uint64_t)b0; rp.noise = sp.noise;
+      rp.noise_iter_stride = sp.noise_iter_stride; rp.cond_scale = cond_scale;
+      CK(launch_set_run_params(pl->d_run, rp, s));
       sp.B = Bc; sp.P = P; sp.L = L; sp.n_iters = n_iters; sp.noise_stream = -1; sp.out = nullptr; sp.tokens = nullptr; sp.clamp = clamp;
       if (pl->use_graph && !pl->taps_on) {
         // one captured iteration, replayed n_iters times; all per-iteration data is device resident
-        std::vector<long long> key = {Bc, n_ctx, cfg ? 1 : 0, (long long)(uintptr_t)sp.noise, sp.noise_iter_stride,
-                                      (long long)n_iters, (long long)(cond_scale * 65536.0), single_call ? 1 : 0};
+        std::vector<long long> key = {Bc, n_ctx, cfg ? 1 : 0, sp.noise ? 1 : 0, (long long)n_iters, single_call ? 1 : 0};
         auto it = pl->graphs.find(key);
         if (it == pl->graphs.end()) {
           if (pl->graphs.size() > 16) { for (auto& kv : pl->graphs) cudaGraphExecDestroy(kv.second.exec); pl->graphs.clear(); }
@@ -1361,17 +1386,16 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
           try { run_iteration(*pl, sp, Beff, Bc, n_ctx, single_call, cs); }
           catch (...) { cudaStreamEndCapture(cs, &graph); if (graph) cudaGraphDestroy(graph); cudaStreamDestroy(cs); throw; }
           CK(cudaStreamEndCapture(cs, &graph));
+          const long long captured = pl->launches - before;   // kernels (and copies) recorded into one iteration
           pl->launches = before;
           cudaGraphExec_t exec = nullptr;
           CK(cudaGraphInstantiate(&exec, graph, 0));
           CK(cudaGraphDestroy(graph));
           CK(cudaStreamDestroy(cs));
-          it = pl->graphs.emplace(key, mdt_plan::GraphEntry{exec}).first;
+          it = pl->graphs.emplace(key, mdt_plan::GraphEntry{exec, captured}).first;
         }
-        long long per_iter = 0;
-        for (const Op& op : pl->unet) { (void)op; per_iter++; }
         for (int i = 0; i < n_iters; ++i) CK(cudaGraphLaunch(it->second.exec, s));
-        pl->launches += (long long)n_iters * (single_call ? per_iter + 2 : 2 * per_iter + 4);
+        pl->launches += (long long)n_iters * it->second.launches;
       } else {
         for (int i = 0; i < n_iters; ++i) run_iteration(*pl, sp, Beff, Bc, n_ctx, single_call, s);
       }
@@ -1403,16 +1427,17 @@ int mdt_plan_inpaint(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const f
     const int P = pl->P, L = pl->L0, R = num_resamples;
     const size_t per = (size_t)P * L;
     const long long draws_per_iter = 2LL * R;              // source noise + R step noises + (R - 1) re-noises
-    CK(cudaStreamSynchronize(s));
+    CK(cudaEventSynchronize(pl->staged));
     memcpy(pl->h_iters, iters, sizeof(IterScalars) * n_iters);
     for (int i = 0; i < n_iters; ++i) { pl->h_tcalls[2 * i] = iters[i].c_noise_a; pl->h_tcalls[2 * i + 1] = iters[i].c_noise_b; }
     CK(cudaMemcpyAsync(pl->d_iters, pl->h_iters, sizeof(IterScalars) * n_iters, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(pl->t_calls, pl->h_tcalls, sizeof(float) * 2 * n_iters, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(pl->staged, s));
     run_time_tables(*pl, 2 * n_iters, s);
     for (int64_t b0 = 0; b0 < B; b0 += pl->Bmax) {
       const int Bc = (int)std::min<int64_t>(pl->Bmax, B - b0);
       const int Beff = cfg ? 2 * Bc : Bc;
-      run_context(*pl, cond_dev + (size_t)b0 * n_ctx, Bc, n_ctx, cfg, s);
+      run_context(*pl, cond_dev + (size_t)b0 * n_ctx * (pl->ctx_pre_encoded ? pl->F : 1), Bc, n_ctx, cfg, s);
       const float* src = source_dev + (size_t)b0 * per;
       const uint8_t* msk = mask_dev + (size_t)b0 * per;
       // draw d of the reference's RNG sequence lives at noise_dev[d][B][P][L]

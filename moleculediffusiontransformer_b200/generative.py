@@ -73,9 +73,12 @@ class _QMBase(nn.Module):
         from .plan import SamplerPlan, default_max_batch, default_precision
 
         precision = precision or default_precision()
-        key = (str(device), precision)
+        device = torch.device(device)
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        device = torch.device("cuda", index)                # 'cuda' and 'cuda:0' are one plan, not two
+        key = (index, precision)
         plan = self._plans.get(key)
-        version = sum(p._version for p in self.parameters())
+        version = self._weights_fingerprint()
         cap = default_max_batch()
         want = cap if batch is None else min(cap, max(8, 1 << (max(int(batch), 1) - 1).bit_length()))
         steps = max(256, 1 << (max(int(timesteps), 2) - 1).bit_length())      # FiLM tables are sized per denoiser call
@@ -86,6 +89,19 @@ class _QMBase(nn.Module):
             plan.weights_version = version
             self._plans[key] = plan
         return plan
+
+    def _weights_fingerprint(self):
+        """Changes whenever a parameter or buffer is re-bound or written through an autograd-visible op.  Writes that bypass the
+        version counter (``p.data.copy_(w)``, an EMA swap through ``.data``) are invisible to PyTorch itself: call
+        ``invalidate_plans()`` after those."""
+        tensors = list(self.parameters()) + list(self.buffers())
+        return hash(tuple((t.data_ptr(), t._version) for t in tensors))
+
+    def invalidate_plans(self):
+        """Drop every packed-weight plan; the next ``sample`` re-packs the current ``state_dict``."""
+        for p in self._plans.values():
+            p.close()
+        self._plans = {}
 
     def _apply(self, fn, *a, **k):  # .to()/.cuda()/.float() invalidate packed weights
         for p in self._plans.values():
@@ -100,20 +116,47 @@ class _QMBase(nn.Module):
         return super().load_state_dict(*a, **k)
 
     # ------------------------------------------------------------------ reference API
+    def set_training_delegate(self, reference_model):
+        """Training (``forward(sequences, output) -> loss``, generative.py:812-833 / 120-143) is not part of the accelerated
+        path.  A user who trains hands over an instance of the reference's own class once; ``forward`` then loads the current
+        ``state_dict`` into it (same keys) and returns its loss.  Call ``sync_from_training_delegate()`` before sampling."""
+        object.__setattr__(self, "_training_delegate", reference_model)
+
+    def sync_from_training_delegate(self):
+        ref = getattr(self, "_training_delegate", None)
+        if ref is None:
+            raise RuntimeError("no training delegate set")
+        self.load_state_dict(ref.state_dict())
+
     def forward(self, sequences, output):
-        raise NotImplementedError("training loss (generative.py:812-833) is outside the accelerated sampling path")
+        ref = getattr(self, "_training_delegate", None)
+        if ref is None:
+            raise NotImplementedError("training loss (generative.py:812-833) is outside the accelerated sampling path; "
+                                      "set_training_delegate(<reference model>) routes it to the reference implementation")
+        if not getattr(self, "_delegate_synced", False):
+            ref.load_state_dict(self.state_dict())
+            object.__setattr__(self, "_delegate_synced", True)
+        return ref(sequences, output)
 
     def _run_sampler(self, *, noise, num_steps, sigma_schedule, sampler, clamp, embedding=None,
                      embedding_scale=1.0, sequences=None, step_noise=None, seed=None, precision=None,
                      return_tokens=False):
-        if sequences is None:
-            raise NotImplementedError(
-                "the accelerated path encodes the conditioning on the device; call model.sample(sequences, ...)")
-        device = noise.device if noise is not None else sequences.device
-        plan = self._plan_for(torch.device(device), precision, batch=sequences.shape[0], timesteps=num_steps)
-        return plan.sample(sequences, noise0=noise, step_noise=step_noise, num_steps=num_steps,
+        # the reference contract (diffusion.py:724-741) passes the encoded conditioning as `embedding=`; `sequences=` (raw
+        # properties, encoded on the device) is the wrapper's own fast path
+        ctx = sequences if sequences is not None else embedding
+        if ctx is None:
+            raise ValueError("one of sequences= (raw conditioning) or embedding= (encoded, [B, n, F]) is required")
+        if sequences is None and embedding.dim() != 3:
+            raise ValueError("embedding= must be the encoded conditioning [B, n, context_embedding_features]")
+        device = noise.device if noise is not None else ctx.device
+        if seed is None and step_noise is None:
+            # fresh ancestral noise per call like the reference's randn_like (diffusion.py:514), reproducible under torch.manual_seed
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        plan = self._plan_for(torch.device(device), precision, batch=ctx.shape[0], timesteps=num_steps)
+        return plan.sample(ctx, noise0=noise, step_noise=step_noise, num_steps=num_steps,
                            sigma_schedule=sigma_schedule, sampler=sampler, clamp=clamp,
-                           cond_scale=float(embedding_scale), seed=seed, return_tokens=return_tokens)
+                           cond_scale=float(embedding_scale), seed=seed, return_tokens=return_tokens,
+                           pre_encoded=sequences is None)
 
     def sample(self, sequences, device, cond_scale=None, timesteps=100, clamp=False, *,
                noise=None, step_noise=None, seed=None, precision=None, return_tokens=False):

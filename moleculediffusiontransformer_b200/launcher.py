@@ -61,8 +61,11 @@ def model_runner(model, device, cond_scale: float, timesteps: int, seed: int, pr
     """run_shard closure over a QMDiffusion / QMDiffusionForward: returns uint8 tokens [rows, L]."""
 
     def run(rows: torch.Tensor, offset: int) -> torch.Tensor:
-        plan = model._plan_for(torch.device(device), precision, batch=rows.shape[0])
         from .diffusion import ADPM2Sampler, KarrasSchedule
+
+        if rows.shape[0] == 0:   # a rank shard_bounds left without rows still takes part in the gather
+            return torch.empty((0, model.max_length), dtype=torch.uint8, device=device)
+        plan = model._plan_for(torch.device(device), precision, batch=rows.shape[0], timesteps=timesteps)
 
         _, tokens = plan.sample(rows, num_steps=timesteps, sigma_schedule=KarrasSchedule(0.001, 9.0, 3.0),
                                 sampler=ADPM2Sampler(1.0), clamp=False, cond_scale=cond_scale, seed=seed,

@@ -79,14 +79,17 @@ class SamplerPlan:
             keep.append(t)
             arr[i].name, arr[i].data, arr[i].numel = k.encode(), t.data_ptr(), t.numel()
         handle = C.c_void_p()
-        _capi.check(self.lib.mdt_plan_create(C.byref(self.cfg), arr, len(sd), self.index, C.byref(handle)))
+        with torch.cuda.device(self.device):   # plan creation must not move the process's current device
+            _capi.check(self.lib.mdt_plan_create(C.byref(self.cfg), arr, len(sd), self.index, C.byref(handle)))
         self.handle = handle
+        self.ctx_features = model.unet.cfg.context_embedding_features
         self.weights_version = None
 
     # ------------------------------------------------------------------
     def close(self):
         if getattr(self, "handle", None):
-            self.lib.mdt_plan_destroy(self.handle)
+            with torch.cuda.device(self.device):
+                self.lib.mdt_plan_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -116,11 +119,20 @@ class SamplerPlan:
 
     def sample(self, sequences, *, noise0=None, step_noise=None, num_steps: int, sigma_schedule, sampler,
                clamp: bool, cond_scale: float, seed: Optional[int] = None, sample_offset: int = 0,
-               return_tokens: bool = False):
+               return_tokens: bool = False, pre_encoded: bool = False):
+        """`sequences` is the raw conditioning [B, n] or, with ``pre_encoded``, the encoded embedding [B, n, F]."""
         if num_steps > self.max_timesteps:
             raise ValueError(f"timesteps={num_steps} exceeds this plan's max_timesteps={self.max_timesteps}")
-        b, n_ctx = sequences.shape
+        if pre_encoded:
+            if sequences.dim() != 3 or sequences.shape[2] != self.ctx_features:
+                raise ValueError(f"embedding must have shape [B, n, {self.ctx_features}]")
+            b, n_ctx = sequences.shape[:2]
+        else:
+            b, n_ctx = sequences.shape
         P, L = self.pred_dim, self.max_length
+        if b == 0:   # an empty shard: nothing to launch (mdt_plan_sample would reject the null data pointer)
+            out = torch.empty((0, P, L), dtype=torch.float32, device=self.device)
+            return (out, torch.empty((0, L), dtype=torch.uint8, device=self.device)) if return_tokens else out
         table = np.ascontiguousarray(self.iter_scalars(num_steps, sigma_schedule, sampler))
         assert table.shape[1] == len(ITER_SCALAR_FIELDS) and table.dtype == np.float32
         with torch.cuda.device(self.device):
@@ -133,6 +145,7 @@ class SamplerPlan:
                 raise ValueError(f"step_noise must have shape {(num_steps - 1, b, P, L)}")
             out = torch.empty((b, P, L), dtype=torch.float32, device=self.device)
             tokens = torch.empty((b, L), dtype=torch.uint8, device=self.device) if return_tokens else None
+            _capi.check(self.lib.mdt_plan_set_context_mode(self.handle, int(bool(pre_encoded))))
             _capi.check(self.lib.mdt_plan_sample(
                 self.handle, cond.data_ptr(), n_ctx, n0.data_ptr() if n0 is not None else None,
                 sn.data_ptr() if sn is not None else None, table.ctypes.data, table.shape[0],

@@ -36,12 +36,12 @@ def generate_and_score(inverse, forward, sequences: torch.Tensor, device, *, con
     """Generate molecules for ``sequences`` with the inverse model and re-predict their properties with the forward model.
 
     Returns ``(tokens uint8 [B, L], predicted float32 [B, pred_dim_fwd, max_length_fwd])``; everything stays on ``device``."""
-    _, tokens = inverse.sample(sequences, device, cond_scale=cond_scale, timesteps=timesteps, seed=seed if seed is not None else 0,
+    _, tokens = inverse.sample(sequences, device, cond_scale=cond_scale, timesteps=timesteps, seed=seed,
                                precision=precision, return_tokens=True)
     ctx = forward.unet.fixed_embedding.max_length
     cond = tokens_to_forward_conditioning(tokens, ctx, x_norm_factor)
     pred = forward.sample(cond, device, cond_scale=1.0, timesteps=forward_timesteps or timesteps,
-                          seed=(seed if seed is not None else 0) + 1, precision=precision)
+                          seed=None if seed is None else seed + 1, precision=precision)
     return tokens, pred
 
 
