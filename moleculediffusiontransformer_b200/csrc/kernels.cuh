@@ -223,6 +223,28 @@ bool gemm_attn_umma_supported(int kind, int C, int L, int heads, int d, int cros
 cudaError_t init_gemm_attn_umma();
 cudaError_t launch_gemm_attn_umma(const void* tmA, const void* tmB, const GemmAttnParams& p, int kind, cudaStream_t s);
 
+// ---- one whole attention layer (gemm_attn_layer.cu): projection -> attention -> out-projection + bias + residual -----------
+struct AttnLayerParams {
+  GemmAttnParams a;        // projection + attention core as in gemm_attn.cu (att / ldo unused: head outputs go to the scratch slots)
+  int Cout;                // out-projection width (the model width C)
+  const float* bias_o;     // [Cout] (to_out bias, v bias folded in for self-attention)
+  const float* res; int ldres;   // residual: the fp32 token stream (may alias C32)
+  float* C32; int ldc;     // fp32 output
+  void* Cop; int ldcop;    // operand-dtype copy of the output (the next GEMM's A operand) or null
+  void* scratch;           // [SMs][attn_layer_slots(heads)][128][d] operand dtype: CTA-private head-output slots (L2 resident)
+  int nslot;               // filled by the launcher from here on
+  int nst, stage_bytes, nacc; unsigned tmem_cols;
+};
+bool attn_layer_supported(int kind, int C, int L, int heads, int d, int cross, int Cout);
+size_t attn_layer_scratch_bytes(int kind, int heads, int d);
+int attn_layer_sms();
+int attn_layer_slots(int heads);   // scratch slots per CTA
+cudaError_t init_attn_layer();
+// tmA: activation map, tmB: per-head projection weights (as launch_gemm_attn); tmS: scratch viewed as [SMs][slots * 128][d];
+// tmW: out-projection weight [Cout][heads * d] with a (KCH x Cout) box
+cudaError_t launch_attn_layer(const void* tmA, const void* tmB, const void* tmS, const void* tmW, const AttnLayerParams& p, int kind,
+                              cudaStream_t s);
+
 // ---- fused FeedForward (gemm_ff.cu): Linear -> GELU -> Linear + residual, hidden activation stays on chip ---------
 struct GemmFFParams {
   int M, C, mid;          // rows, model width, hidden width (mid = C * multiplier)

@@ -57,7 +57,7 @@ struct MdtError {
 // ------------------------------------------------------------------------------------------------
 // program representation
 // ------------------------------------------------------------------------------------------------
-enum OpType { OP_GEMM, OP_GN_STATS, OP_ROW_STATS, OP_ATTN, OP_UPGATHER, OP_PERMUTE, OP_GN_APPLY, OP_LN_APPLY, OP_GEMM_TMA, OP_GEMM_ATTN, OP_DUP_ROWS, OP_GEMM_FF };
+enum OpType { OP_GEMM, OP_GN_STATS, OP_ROW_STATS, OP_ATTN, OP_UPGATHER, OP_PERMUTE, OP_GN_APPLY, OP_LN_APPLY, OP_GEMM_TMA, OP_GEMM_ATTN, OP_DUP_ROWS, OP_GEMM_FF, OP_ATTN_LAYER };
 
 struct Op {
   OpType type = OP_GEMM;
@@ -71,9 +71,11 @@ struct Op {
   TmaGemmParams tg{};
   GemmAttnParams gat{};
   GemmFFParams gff{};
+  AttnLayerParams al{};
   alignas(64) unsigned char tmA[128];
   alignas(64) unsigned char tmB[128];
   alignas(64) unsigned char tmC[128];
+  alignas(64) unsigned char tmD[128];
   bool cross = false;  // attention reads the precomputed conditioning K/V
   bool umma_core = false;  // fused attention with the softmax-attention core on tcgen05 (gemm_attn_umma.cu)
   int cross_layer = -1;
@@ -135,6 +137,7 @@ struct mdt_plan {
   float *emb = nullptr, *emb_stats = nullptr, *emb_null = nullptr, *emb_null_stats = nullptr;
   float *qkv = nullptr, *att = nullptr, *qc = nullptr, *ff = nullptr, *upy = nullptr;
   float *gn_stats = nullptr, *row_stats = nullptr;
+  void* attn_scratch = nullptr;   // CTA-private head-output slots of the fused attention-layer kernel (gemm_attn_layer.cu)
   // time path
   float *t_calls = nullptr, *t_feat = nullptr, *t_a = nullptr, *t_b = nullptr, *t_map = nullptr;
   const float *w_time_freq = nullptr, *w_time = nullptr, *b_time = nullptr, *w_map0 = nullptr, *b_map0 = nullptr,
@@ -370,6 +373,48 @@ struct Builder {
     emit(prog, op);
   }
 
+  // whole attention layer in one kernel (gemm_attn_layer.cu): projection + attention + out-projection + bias + residual into t
+  // (and the operand copy `cop` of the new token stream when the next op reads it raw)
+  bool layer_ok(int C, int L, int cross, bool packed_cross) const {
+    if (pl.prec == MDT_PREC_FP32 || getenv("MDT_NO_FUSED_LAYER")) return false;
+    // measured on the README model at B = 4096 (profiles/README.md): the fused layer wins where the (rows x heads*d) attention tensor
+    // would not fit L2 (level 1: 256 vs 293 us self, 259 vs 272 us cross) and loses at level 2, where only 256 row blocks exist for
+    // 148 SMs and the unfused pair keeps its intermediate in L2 anyway (131 vs 113 us); default: width <= 128 only
+    const char* mc = getenv("MDT_FUSED_LAYER_MAXC");
+    if (C > (mc ? atoi(mc) : 128)) return false;
+    if (cross && !packed_cross) return false;
+    return attn_layer_supported(pl.prec, C, L, pl.cfg.heads, pl.cfg.head_features, cross, C);
+  }
+  void emit_attn_layer(std::vector<Op>& prog, const void* A, int C, int L, const float* dW32, const float* bias_q, int cross,
+                       int cross_layer, const void* kn_flag, const void* kvf_c, const void* kvf_n, const float* dWo32,
+                       const float* bias_o, float* t, void* cop) {
+    Op op; op.type = OP_ATTN_LAYER; op.rps = L; op.cross = cross != 0; op.cross_layer = cross_layer;
+    const int kch = pl.prec == MDT_PREC_TF32 ? 32 : 64;
+    const int heads = pl.cfg.heads, d = pl.cfg.head_features, BN = cross ? d : 3 * d, Hd = heads * d;
+    AttnLayerParams& y = op.al;
+    GemmAttnParams& g = y.a;
+    g.M = 0; g.heads = heads; g.d = d; g.kchunks = C / kch; g.C = C; g.L = L; g.Sb = 128 / L; g.cross = cross;
+    g.bias = bias_q; g.scale = 1.0f / sqrtf((float)d); g.att = nullptr; g.ldo = 0;
+    g.kc = nullptr; g.kn = kn_flag; g.ldkv = 2 * Hd; g.kv_sample_stride = 0; g.n_cond = 0; g.nk = L; g.kv_fp32 = 1;
+    g.kvf_c = kvf_c; g.kvf_n = kvf_n;
+    const char* ps = getenv("MDT_PACK_SELF");
+    g.pack_self = (!cross && L >= 2 && L <= 8 && !(ps && ps[0] == '0')) ? 1 : 0;
+    y.Cout = C; y.bias_o = bias_o; y.res = t; y.ldres = C; y.C32 = t; y.ldc = C; y.Cop = cop; y.ldcop = C;
+    if (!pl.attn_scratch) {
+      const size_t bytes = attn_layer_scratch_bytes(pl.prec, heads, d);
+      pl.attn_scratch = dalloc((bytes + 3) / 4);
+      CK(cudaMemset(pl.attn_scratch, 0, bytes));
+    }
+    y.scratch = pl.attn_scratch;
+    const void* wop = tc_copy(dW32, (size_t)heads * BN * C);
+    const void* woo = tc_copy(dWo32, (size_t)C * Hd);
+    if (make_tmap_act(op.tmA, A, pl.prec, C, L, (long long)pl.Beff_max) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(layer activation) failed");
+    if (make_tmap_weight(op.tmB, wop, pl.prec, (long long)C, heads * BN, BN) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(layer weight) failed");
+    if (make_tmap_act(op.tmC, pl.attn_scratch, pl.prec, d, attn_layer_slots(heads) * 128, (long long)attn_layer_sms()) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(layer scratch) failed");
+    if (make_tmap_weight(op.tmD, woo, pl.prec, (long long)Hd, C, C) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(layer out-projection) failed");
+    emit(prog, op);
+  }
+
   // ResnetBlock1d (modules.py:145-205).  Returns the output buffer (acquired from the pool).
   float* resnet(std::vector<Op>& prog, const std::string& pre, const Src& in, int L, int Cout, int groups,
                 float* forced_out = nullptr, void** out_op = nullptr) {
@@ -520,6 +565,7 @@ struct Builder {
         }
         const float* d_w = upload(w); const float* d_b = upload(b);
         const bool fuse_self = fast && fuse_attn && gemm_attn_supported(pl.prec, C, L, heads, d, 0, 0);
+        const float* d_wr_self = nullptr; const float* d_bq_self = nullptr; bool layer_self = false;
         if (fuse_self) {
           // head-major repack: rows [h][q(64) | k(64) | v(64)]
           std::vector<float> wr((size_t)3 * Hd * C), br((size_t)3 * Hd);
@@ -530,10 +576,11 @@ struct Builder {
                 memcpy(&wr[dst * C], &w[src * C], (size_t)C * sizeof(float));
                 br[dst] = b[src];
               }
-          const float* d_wr = upload(wr);
-          const float* d_bq = upload(b.data(), Hd);      // q bias only (see gemm_attn.cu)
+          d_wr_self = upload(wr);
+          d_bq_self = upload(b.data(), Hd);      // q bias only (see gemm_attn.cu)
           emit_ln_apply(prog, t, C, L, tn);
-          emit_gemm_attn(prog, tn, C, L, d_wr, d_bq, 0, -1, nullptr, nullptr);
+          layer_self = layer_ok(C, L, 0, false);
+          if (!layer_self) emit_gemm_attn(prog, tn, C, L, d_wr_self, d_bq_self, 0, -1, nullptr, nullptr);
         } else if (fast) {
           emit_ln_apply(prog, t, C, L, tn);
           emit_gemm_tma(prog, tn, C, L, 1, d_w, d_b, 3 * Hd, 0, nullptr, nullptr, pl.qkv);
@@ -564,7 +611,10 @@ struct Builder {
           }
         }
         const float* d_bo = upload(bo);
-        if (fast) {
+        if (layer_self) {
+          emit_attn_layer(prog, tn, C, L, d_wr_self, d_bq_self, 0, -1, nullptr, nullptr, nullptr, d_wo, d_bo, t,
+                          has_cross ? nullptr : (void*)tn);
+        } else if (fast) {
           // without a cross-attention stage the raw operand copy of the new token stream feeds FF1 directly
           emit_gemm_tma(prog, pl.att, Hd, L, 1, d_wo, d_bo, C, 0, t, t, has_cross ? nullptr : (void*)tn);
         } else {
@@ -603,7 +653,10 @@ struct Builder {
         }
         const int layer = (int)pl.cross.size();
         pl.cross.push_back(cl);
-        if (fuse_cross) {
+        const bool layer_cross = fuse_cross && layer_ok(C, L, 1, packed);
+        if (layer_cross) {
+          emit_ln_apply(prog, t, C, L, tn);
+        } else if (fuse_cross) {
           emit_ln_apply(prog, t, C, L, tn);
           // row-major variant: the fused kernel streams fp32 K/V with cp.async in both tensor-core modes (tf32: rounded copy, bf16: the
           // fp32 cache); the null-branch pointer doubles as the "has a null branch" flag, so it is passed in the packed variant too
@@ -632,7 +685,9 @@ struct Builder {
         if (!fuse_cross) emit(prog, at);
         const float* d_wo = upload(T(ap + "attention.to_out.weight", (int64_t)C * Hd), (size_t)C * Hd);
         const float* d_bo = upload(T(ap + "attention.to_out.bias", C), C);
-        if (fast) {
+        if (layer_cross) {
+          emit_attn_layer(prog, tn, C, L, d_wq, d_bq, 1, layer, cl.kv_null, cl.kvf_cond, cl.kvf_null, d_wo, d_bo, t, tn);
+        } else if (fast) {
           emit_gemm_tma(prog, pl.att, Hd, L, 1, d_wo, d_bo, C, 0, t, t, tn);
         } else {
           Src as{pl.att, Hd, nullptr, 0, 1.f};
@@ -927,6 +982,7 @@ static std::string describe(const Op& op, int Beff) {
     case OP_GEMM_TMA: snprintf(b, sizeof b, "gemm_tma  M=%d N=%d K=%dx%d L=%d bn=%d%s%s%s%s", Beff * op.rps, op.tg.N, op.tg.taps, op.tg.C, op.tg.L, op.tg.BN,
                                op.tg.gn_L ? " +gn" : "", op.tg.res ? " +res" : "", op.tg.act ? " +act" : "", h); break;
     case OP_GEMM_ATTN: snprintf(b, sizeof b, "gemm_attn%s %s M=%d C=%d L=%d%s", op.umma_core ? "_umma" : "", op.cross ? "cross" : "self", Beff * op.rps, op.gat.C, op.gat.L, h); break;
+    case OP_ATTN_LAYER: snprintf(b, sizeof b, "attn_layer %s M=%d C=%d L=%d%s%s", op.cross ? "cross" : "self", Beff * op.rps, op.al.a.C, op.al.a.L, op.al.Cop ? " +cop" : "", h); break;
     case OP_GEMM: snprintf(b, sizeof b, "gemm      M=%d N=%d K=%d taps=%d stride=%d%s", Beff * op.rps, op.g.N, op.g.K, op.g.a.taps, op.g.a.stride, h); break;
     case OP_GN_APPLY: snprintf(b, sizeof b, "gn_apply  B=%d L=%d C=%d%s%s", Beff, op.ga.L, op.ga.c0 + op.ga.c1, op.ga.raw ? " +raw" : "", h); break;
     case OP_LN_APPLY: snprintf(b, sizeof b, "ln_apply  rows=%d C=%d%s", Beff * op.rps, op.la.C, h); break;
@@ -962,7 +1018,8 @@ static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_con
   for (Op& op : prog) {
     Beff = op.half ? n_cond : Beff_full;
     if (timed) CK(cudaEventRecord(ev0, s));
-    const bool streams = op.type == OP_GEMM_TMA || op.type == OP_GEMM_ATTN || op.type == OP_GN_APPLY || op.type == OP_LN_APPLY;
+    const bool streams = op.type == OP_GEMM_TMA || op.type == OP_GEMM_ATTN || op.type == OP_GN_APPLY || op.type == OP_LN_APPLY ||
+                         op.type == OP_ATTN_LAYER;
     rev = (serp && streams) ? (rev ^ 1) : 0;
     switch (op.type) {
       case OP_DUP_ROWS: {
@@ -987,6 +1044,12 @@ static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_con
         GemmAttnParams g = op.gat; g.M = Beff * op.rps; g.rev = rev;
         if (op.cross) { g.nk = n_ctx; g.kv_sample_stride = (long long)n_ctx * g.ldkv; g.n_cond = n_cond; }
         CK(op.umma_core ? launch_gemm_attn_umma(op.tmA, op.tmB, g, pl.prec, s) : launch_gemm_attn(op.tmA, op.tmB, g, pl.prec, s));
+        pl.launches++; break;
+      }
+      case OP_ATTN_LAYER: {
+        AttnLayerParams y = op.al; y.a.M = Beff * op.rps; y.a.rev = rev;
+        if (op.cross) { y.a.nk = n_ctx; y.a.kv_sample_stride = (long long)n_ctx * y.a.ldkv; y.a.n_cond = n_cond; }
+        CK(launch_attn_layer(op.tmA, op.tmB, op.tmC, op.tmD, y, pl.prec, s));
         pl.launches++; break;
       }
       case OP_GEMM_FF: { GemmFFParams g = op.gff; g.M = Beff * op.rps; CK(launch_gemm_ff(op.tmA, op.tmB, op.tmC, g, pl.prec, s)); pl.launches++; break; }
@@ -1176,6 +1239,7 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
     CK(init_gemm_tma());
     CK(init_gemm_attn());
     CK(init_gemm_attn_umma());
+    CK(init_attn_layer());
     CK(init_gemm_ff());
     pl->cfg = *cfg; pl->device = device; pl->prec = cfg->precision;
     pl->P = cfg->in_channels; pl->L0 = cfg->length; pl->Hd = cfg->heads * cfg->head_features; pl->F = cfg->ctx_features;
