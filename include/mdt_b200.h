@@ -144,6 +144,13 @@ int mdt_plan_sample(mdt_plan* plan, const float* cond_dev, int32_t n_ctx, const 
  * diffusion.py:724-741) -- instead of the raw `sequences` [B, n_ctx]; the device-side encoder is skipped.  Default 0. */
 int mdt_plan_set_context_mode(mdt_plan* plan, int pre_encoded);
 
+/* Sampler mode of mdt_plan_sample.  0 (default): the rows describe ADPM2Sampler / AEulerSampler iterations (see above).
+ * 1: KarrasSampler (diffusion.py:399-453): rows carry sigma = sigma_hat, sigma_mid = sigma_next, dt_mid = sigma_next - sigma_hat,
+ * dt_down = 0.5 (sigma - sigma_hat) and sigma_up = the noise scale sqrt(sigma_hat^2 - sigma^2) s_noise of the NEXT step; the second
+ * update is x_hat + dt_down (d + d'), the step noise of iteration i is drawn ahead of its first denoiser call (slot i of
+ * step_noise_dev / Philox stream i + 1) and `init_noise_scale` is the scale of step 0. */
+int mdt_plan_set_sampler_mode(mdt_plan* plan, int mode, float init_noise_scale);
+
 /* Inpainting: replaces QMDiffusion.inpaint -> XDiffusion_x.inpaint -> DiffusionInpainter.forward ->
  * ADPM2Sampler.inpaint (generative.py:871-914, diffusion.py:744-767, 612-625, 526-549).
  *   source_dev [B, P, L] fp32   the draft to keep where mask != 0;   mask_dev [B, P, L] uint8

@@ -14,7 +14,7 @@ EXPORTS = [
     "mdt_last_error", "mdt_abi_version", "mdt_device_count", "mdt_adpm2_scalars", "mdt_aeuler_scalars", "mdt_karras_sigmas",
     "mdt_plan_create", "mdt_plan_destroy", "mdt_plan_device_bytes", "mdt_plan_launch_count", "mdt_plan_sample",
     "mdt_plan_inpaint", "mdt_plan_unet_forward", "mdt_plan_enable_taps", "mdt_plan_read_tap", "mdt_op_linear", "mdt_op_step_update",
-    "mdt_op_decode_tokens", "mdt_plan_set_context_mode",
+    "mdt_op_decode_tokens", "mdt_plan_set_context_mode", "mdt_plan_set_sampler_mode",
 ]
 
 
@@ -80,6 +80,7 @@ def load() -> C.CDLL:
     lib.mdt_plan_inpaint.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, u64, u64, i64, f32, vp, vp]
     lib.mdt_plan_unet_forward.argtypes = [vp, vp, f32, vp, i32, i64, f32, vp, vp]
     lib.mdt_plan_set_context_mode.argtypes = [vp, C.c_int]
+    lib.mdt_plan_set_sampler_mode.argtypes = [vp, C.c_int, f32]
     lib.mdt_plan_enable_taps.argtypes = [vp, C.c_int]
     lib.mdt_plan_read_tap.argtypes = [vp, C.c_char_p, vp, i64]
     lib.mdt_plan_read_tap.restype = i64

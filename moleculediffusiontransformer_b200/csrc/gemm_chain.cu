@@ -9,8 +9,8 @@
 // TMA-loads the hidden block from that scratch as its A operand and accumulates [128, C] in its own TMEM columns; the final
 // epilogue adds bias and residual and writes the fp32 token stream plus the operand-dtype copy the next GEMM reads.  Neither the
 // (rows x mid) hidden tensor nor a separate LayerNorm pass touches HBM.
-// The second GEMM of block k is queued behind the first tile of block k + 1 (ring order J(k+1,0), O(k), J(k+1,1), ...) and its
-// epilogue runs after that tile's, so its operand loads hide under epilogue work.
+// The second GEMM of block k is queued behind the first-GEMM tiles of block k + 1 (ring order J(k+1,0..T-1), O(k), J(k+2,0), ...)
+// and its epilogue runs after theirs, so its operand loads stream while the epilogue warps are busy and nothing waits on L2 latency.
 //
 //   warp 0      TMA producer (one lane)            warp 1     tcgen05.mma issuer, owns TMEM
 //   warps 2-17  epilogue: TMEM quadrant q = warp % 4, column group cg = (warp - 2) / 4 (32 columns of a 128-column tile)
@@ -29,7 +29,7 @@ constexpr int C_EPI_WARPS = 16;
 constexpr int C_THREADS = 64 + 32 * C_EPI_WARPS;
 constexpr int C_LD = 36;                                    // transposition tile stride (32 + 4 floats)
 constexpr int C_STG_BYTES = C_EPI_WARPS * 32 * C_LD * 4;    // one 32 x 32 tile per epilogue warp
-constexpr int C_XCH_BYTES = C_TM * 8 * 2 * 4;               // LayerNorm exchange: [128 rows][8 column chunks][mean, M2]
+constexpr int C_XCH_BYTES = 2 * C_TM * 8 * 2 * 4;           // LayerNorm exchange, double buffered by block parity: [2][128 rows][8 column chunks][mean, M2]
 
 __device__ __forceinline__ void fence_proxy_async_glob() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -41,7 +41,8 @@ __device__ __forceinline__ void store_op_f4(void* base, size_t idx, float4 v) {
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
 }
 
-template <int KIND>
+// NCH = 32-column chunks of the output tile per epilogue warp: 1 for C = 128, 2 for C = 256
+template <int KIND, int NCH>
 __global__ void __launch_bounds__(C_THREADS, 1) ff_chain_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB0,
                                                                const __grid_constant__ CUtensorMap tmS,
@@ -103,7 +104,6 @@ __global__ void __launch_bounds__(C_THREADS, 1) ff_chain_kernel(const __grid_con
       for (int k = 0; k < nk_cta; ++k) {
         const int blk = block_of_k(k);
         for (int nt = 0; nt < T; ++nt) {
-          if (nt == 1 && k > 0) load_second(k - 1);
           for (int kc = 0; kc < k1c; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* sa = smem + stage * stage_bytes;
@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) ff_chain_kernel(const __grid_con
             if (++stage == NST) { stage = 0; phase ^= 1u; }
           }
         }
+        if (k > 0) load_second(k - 1);     // one whole block behind: its operands stream while block k's tiles are in the epilogue
       }
       if (nk_cta > 0) load_second(nk_cta - 1);
     }
@@ -141,7 +142,6 @@ __global__ void __launch_bounds__(C_THREADS, 1) ff_chain_kernel(const __grid_con
     };
     for (int k = 0; k < nk_cta; ++k) {
       for (int nt = 0; nt < T; ++nt, ++j) {
-        if (nt == 1 && k > 0) mma_second(k - 1);
         const int buf = j & 1;
         mbar_wait(&acc_empty[buf], ((uint32_t)(j >> 1) & 1u) ^ 1u);
         tc_fence_after();
@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) ff_chain_kernel(const __grid_con
           if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
       }
+      if (k > 0) mma_second(k - 1);
     }
     if (nk_cta > 0) mma_second(nk_cta - 1);
   } else {
@@ -173,27 +174,27 @@ __global__ void __launch_bounds__(C_THREADS, 1) ff_chain_kernel(const __grid_con
     float2* xch = reinterpret_cast<float2*>(smem + NST * stage_bytes + C_STG_BYTES);    // [128][8]
     const int cl = (lane & 7) * 4, r0 = lane >> 3;      // coalesced layout: 8 lanes per 128-byte row segment, 4 rows per pass
     const size_t scr_cta = (size_t)blockIdx.x * 2 * C_TM;
-    const int nch = C >> 7;                 // 32-column chunks of the output tile per warp (1 for C = 128, 2 for C = 256)
+    constexpr int nch = NCH;
     const int nchunks_row = C >> 5;
 
     auto final_epilogue = [&](int kk) {
       const int m0 = block_of_k(kk) * C_TM + q * 32;
-      float4 r[2][8];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      float4 r[NCH][8];
+      auto load_res = [&](int u) {
         const int no = (cg * nch + u) * 32 + cl;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int mo = m0 + r0 + i * 4;
-          r[u][i] = (p.res && u < nch && mo < p.M) ? *reinterpret_cast<const float4*>(p.res + (size_t)mo * p.ldres + no)
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          r[u][i] = (p.res && mo < p.M) ? *reinterpret_cast<const float4*>(p.res + (size_t)mo * p.ldres + no) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      }
+      };
+      load_res(0);          // issued ahead of the accumulator wait: the HBM latency of the residual hides behind it
       mbar_wait(&out_full, (uint32_t)kk & 1u);
       tc_fence_after();
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (u < nch) {
+      for (int u = 0; u < NCH; ++u) {
+        {
+          if (u > 0) load_res(u);
           const int col0 = (cg * nch + u) * 32;
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
@@ -223,10 +224,12 @@ __global__ void __launch_bounds__(C_THREADS, 1) ff_chain_kernel(const __grid_con
       if (lane == 0) mbar_arrive(&out_empty);
       if (p.Cop && p.cop_ln) {
         // LayerNorm over the C columns of every row (no affine: folded into the consumer's weights).  Per 32-column chunk the
-        // eight lanes of a row hold it entirely: exact local mean and centred sum of squares, then Chan's merge across chunks.
+        // eight lanes of a row hold it entirely: exact local mean and centred sum of squares, then the equal-count form of
+        // Chan's merge across chunks:  mean = avg(mean_c),  M2 = sum(M2_c) + 32 * sum((mean_c - mean)^2).
+        float2* xb = xch + (size_t)(kk & 1) * C_TM * 8;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (u < nch) {
+        for (int u = 0; u < NCH; ++u) {
+          {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 o = r[u][i];
@@ -236,34 +239,32 @@ __global__ void __launch_bounds__(C_THREADS, 1) ff_chain_kernel(const __grid_con
               const float dx = o.x - mean, dy = o.y - mean, dz = o.z - mean, dw = o.w - mean;
               float m2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
               m2 += __shfl_xor_sync(0xffffffffu, m2, 1); m2 += __shfl_xor_sync(0xffffffffu, m2, 2); m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
-              if ((lane & 7) == 0) xch[(q * 32 + r0 + i * 4) * 8 + cg * nch + u] = make_float2(mean, m2);
+              if ((lane & 7) == 0) xb[(q * 32 + r0 + i * 4) * 8 + cg * nch + u] = make_float2(mean, m2);
             }
           }
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");      // the four column-group warps of this quadrant
+        const float inv_chunks = 1.0f / (float)nchunks_row, inv_c = 1.0f / (float)C;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int row = q * 32 + r0 + i * 4;
-          float mean = 0.f, m2 = 0.f, n = 0.f;
-          for (int c = 0; c < nchunks_row; ++c) {
-            const float2 e = xch[row * 8 + c];
-            const float nn = n + 32.0f, dl = e.x - mean;
-            mean += dl * (32.0f / nn);
-            m2 += e.y + dl * dl * (n * 32.0f / nn);
-            n = nn;
-          }
-          const float rstd = 1.0f / sqrtf(m2 / n + p.ln_eps);
+          const float2* e = xb + (q * 32 + r0 + i * 4) * 8;
+          float msum = 0.f, m2 = 0.f;
+          for (int c = 0; c < nchunks_row; ++c) { msum += e[c].x; m2 += e[c].y; }
+          const float mean = msum * inv_chunks;
+          float dev = 0.f;
+          for (int c = 0; c < nchunks_row; ++c) { const float dl = e[c].x - mean; dev = fmaf(dl, dl, dev); }
+          const float rstd = rsqrtf(fmaf(32.0f, dev, m2) * inv_c + p.ln_eps);
           const int mo = m0 + r0 + i * 4;
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (u < nch && mo < p.M) {
+          for (int u = 0; u < NCH; ++u) {
+            if (mo < p.M) {
               const float4 o = r[u][i];
               store_op_f4<KIND>(p.Cop, (size_t)mo * p.ldcop + (cg * nch + u) * 32 + cl,
                                 make_float4((o.x - mean) * rstd, (o.y - mean) * rstd, (o.z - mean) * rstd, (o.w - mean) * rstd));
             }
           }
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");      // exchange slots are free again
+        // no second barrier: the exchange buffer of the other parity is used next, and the barrier of that block orders its reuse
       }
     };
 
@@ -296,8 +297,8 @@ __global__ void __launch_bounds__(C_THREADS, 1) ff_chain_kernel(const __grid_con
           fence_proxy_async_glob();      // publish this thread's hidden values of the block to the async proxy
           mbar_arrive(&h_ready);
         }
-        if (nt == 0 && k > 0) final_epilogue(k - 1);
       }
+      if (k > 0) final_epilogue(k - 1);
     }
     if (nk_cta > 0) final_epilogue(nk_cta - 1);
   }
@@ -347,9 +348,11 @@ bool ff_chain_supported(int kind, int C, int mid, int L) {
 size_t ff_chain_scratch_bytes(int kind, int mid) { return (size_t)ff_chain_sms() * 2 * tc::C_TM * mid * (kind == 1 ? 4 : 2); }
 
 cudaError_t init_ff_chain() {
-  cudaError_t e = cudaFuncSetAttribute(tc::ff_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM_LIMIT);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(tc::ff_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM_LIMIT);
+  cudaError_t e = cudaFuncSetAttribute(tc::ff_chain_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM_LIMIT);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::ff_chain_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM_LIMIT);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::ff_chain_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM_LIMIT);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::ff_chain_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM_LIMIT);
+  return e;
 }
 
 cudaError_t launch_ff_chain(const void* tmA, const void* tmB0, const void* tmS, const void* tmW, const FFChainParams& pin, int kind,
@@ -368,8 +371,10 @@ cudaError_t launch_ff_chain(const void* tmA, const void* tmB0, const void* tmS, 
   const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(tmB0);
   const CUtensorMap& sc = *reinterpret_cast<const CUtensorMap*>(tmS);
   const CUtensorMap& w = *reinterpret_cast<const CUtensorMap*>(tmW);
-  if (kind == 1) tc::ff_chain_kernel<1><<<grid, tc::C_THREADS, smem, s>>>(a, b, sc, w, p, idesc1, idesc2);
-  else tc::ff_chain_kernel<2><<<grid, tc::C_THREADS, smem, s>>>(a, b, sc, w, p, idesc1, idesc2);
+  if (kind == 1 && p.C == 128) tc::ff_chain_kernel<1, 1><<<grid, tc::C_THREADS, smem, s>>>(a, b, sc, w, p, idesc1, idesc2);
+  else if (kind == 1) tc::ff_chain_kernel<1, 2><<<grid, tc::C_THREADS, smem, s>>>(a, b, sc, w, p, idesc1, idesc2);
+  else if (p.C == 128) tc::ff_chain_kernel<2, 1><<<grid, tc::C_THREADS, smem, s>>>(a, b, sc, w, p, idesc1, idesc2);
+  else tc::ff_chain_kernel<2, 2><<<grid, tc::C_THREADS, smem, s>>>(a, b, sc, w, p, idesc1, idesc2);
   return cudaGetLastError();
 }
 

@@ -664,8 +664,9 @@ __global__ void step_update_kernel(const StepParams p) {
   const float* noise = p.run ? p.run->noise : p.noise;
   const long long noise_stride = p.run ? p.run->noise_iter_stride : p.noise_iter_stride;
   const float cond_scale = p.run ? p.run->cond_scale : p.cond_scale;
-  if (WHICH == 1 && noise) {
-    const float* nz = noise + (size_t)iter * noise_stride + (size_t)b * n;
+  const bool add_noise = !(p.karras && last);            // karras: the noise added here belongs to the next step; none after the last
+  if (WHICH == 1 && noise && add_noise) {
+    const float* nz = noise + (size_t)(iter + (p.karras ? 1 : 0)) * noise_stride + (size_t)b * n;
     for (int e = threadIdx.x; e < n; e += blockDim.x) { const int pp = e / L, l = e - pp * L; tile[pp * (L + 1) + l] = nz[e]; }
     __syncthreads();
   }
@@ -691,13 +692,15 @@ __global__ void step_update_kernel(const StepParams p) {
     else { const float4 m = *reinterpret_cast<const float4*>(p.xmid + o); cur[0] = m.x; cur[1] = m.y; cur[2] = m.z; cur[3] = m.w; }
     float res[4];
     float nz[4] = {0.f, 0.f, 0.f, 0.f};
-    if (WHICH == 1) {
+    float dslope[4] = {0.f, 0.f, 0.f, 0.f};
+    if (WHICH == 1 && p.karras) { const float4 d4 = *reinterpret_cast<const float4*>(p.daux + o); dslope[0] = d4.x; dslope[1] = d4.y; dslope[2] = d4.z; dslope[3] = d4.w; }
+    if (WHICH == 1 && add_noise) {
       if (noise) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const int e = g * 4 + j; const int l = e / P, pp = e - l * P; nz[j] = tile[pp * (L + 1) + l]; }
       } else {
         const unsigned long long sd = p.run ? p.run->seed : p.seed, so = p.run ? p.run->sample_offset : p.sample_offset;
-        const float4 z = philox_normal4(sd, so + b, p.noise_stream >= 0 ? (unsigned)p.noise_stream : (unsigned)(iter + 1), (unsigned)g);
+        const float4 z = philox_normal4(sd, so + b, p.noise_stream >= 0 ? (unsigned)p.noise_stream : (unsigned)(iter + 1 + (p.karras ? 1 : 0)), (unsigned)g);
         nz[0] = z.x; nz[1] = z.y; nz[2] = z.z; nz[3] = z.w;
       }
     }
@@ -706,9 +709,11 @@ __global__ void step_update_kernel(const StepParams p) {
       float x0 = c_skip * cur[j] + c_out * pred[j];
       x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
       const float dd = (cur[j] - x0) / sig;
-      if (WHICH == 0) res[j] = xv[j] + dd * it.dt_mid;
+      if (WHICH == 0) { res[j] = xv[j] + dd * it.dt_mid; dslope[j] = dd; }
+      else if (p.karras) res[j] = (xv[j] + it.dt_down * (dslope[j] + dd)) + nz[j] * it.sigma_up;   // diffusion.py:433, then the next step's x_hat
       else res[j] = (xv[j] + dd * it.dt_down) + nz[j] * it.sigma_up;
     }
+    if (p.karras && WHICH == 0) *reinterpret_cast<float4*>(p.daux + o) = make_float4(dslope[0], dslope[1], dslope[2], dslope[3]);
     const float4 r4 = make_float4(res[0], res[1], res[2], res[3]);
     if (WHICH == 0) *reinterpret_cast<float4*>(p.xmid + o) = r4;
     else *reinterpret_cast<float4*>(p.x + o) = r4;
@@ -825,6 +830,36 @@ cudaError_t launch_finalize(const float* x, float* out, unsigned char* tokens, i
   if (B <= 0) return cudaSuccess;
   if ((size_t)L * (P + 1) * sizeof(float) > MDT_STEP_SMEM_MAX) return cudaErrorInvalidValue;
   finalize_kernel<<<B, 256, (size_t)L * (P + 1) * sizeof(float), s>>>(x, out, tokens, P, L, clamp);
+  return cudaGetLastError();
+}
+
+// KarrasSampler step 0 (diffusion.py:425-426 on x = sigma_0 * noise): x_hat = x + scale * eps_0, next network input c_in * x_hat.
+__global__ void karras_prenoise_kernel(float* __restrict__ x, float* __restrict__ xin, const float* __restrict__ noise, float scale,
+                                       float c_in, unsigned long long seed, unsigned long long sample_offset, int B, int P, int L, int cfg) {
+  const int b = blockIdx.x, n = P * L;
+  for (int g = threadIdx.x; g < n / 4; g += blockDim.x) {
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!noise) z = philox_normal4(seed, sample_offset + b, 1u, (unsigned)g);
+    const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = g * 4 + j;                 // token-major element: e = l * P + p
+      const int l = e / P, pp = e - l * P;
+      const size_t tm = (size_t)b * n + e;
+      const float nzv = noise ? noise[(size_t)b * n + (size_t)pp * L + l] : zz[j];
+      const float v = x[tm] + scale * nzv;
+      x[tm] = v;
+      xin[tm] = c_in * v;
+      if (cfg) xin[(size_t)B * n + tm] = c_in * v;
+    }
+  }
+}
+
+cudaError_t launch_karras_prenoise(float* x, float* xin, const float* noise, float scale, float c_in, unsigned long long seed,
+                                   unsigned long long sample_offset, int B, int P, int L, int cfg, cudaStream_t s) {
+  if (B <= 0) return cudaSuccess;
+  if ((P * L) % 4) return cudaErrorInvalidValue;
+  karras_prenoise_kernel<<<B, 256, 0, s>>>(x, xin, noise, scale, c_in, seed, sample_offset, B, P, L, cfg);
   return cudaGetLastError();
 }
 

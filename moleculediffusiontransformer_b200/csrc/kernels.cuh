@@ -106,6 +106,9 @@ struct StepParams {
   int B, P, L;
   int n_iters;
   int noise_stream;          // Philox stream id override for the ancestral noise (< 0: iteration + 1)
+  int karras;                // KarrasSampler rows (diffusion.py:399-453): update A keeps its slope d in `daux`, update B is
+                             // x + dt_down * (d + d'), and the noise added afterwards is that of the NEXT step (slot / stream + 1)
+  float* daux;               // [B*L][P] slope of call A (karras only)
   float* out;                // final (B,P,L) result written when the last iteration completes (may be null)
   unsigned char* tokens;     // final argmax tokens [B][L] (may be null)
   int clamp;
@@ -142,6 +145,9 @@ cudaError_t launch_step_init(const float* noise0, float* x, float* xin, const It
                              unsigned long long seed, unsigned long long sample_offset, int B, int P, int L,
                              int cfg, cudaStream_t s);
 cudaError_t launch_step_update(int which, const StepParams& p, cudaStream_t s);
+// KarrasSampler step 0: x += scale * eps_0 (injected (B,P,L) tensor or Philox stream 1), xin = c_in * x (both branches)
+cudaError_t launch_karras_prenoise(float* x, float* xin, const float* noise, float scale, float c_in, unsigned long long seed,
+                                   unsigned long long sample_offset, int B, int P, int L, int cfg, cudaStream_t s);
 cudaError_t launch_finalize(const float* x, float* out, unsigned char* tokens, int B, int P, int L, int clamp,
                             cudaStream_t s);
 cudaError_t launch_inpaint(int mode, float* x, float* xin, const float* source, const unsigned char* mask, const float* noise,
@@ -245,19 +251,27 @@ cudaError_t init_attn_layer();
 cudaError_t launch_attn_layer(const void* tmA, const void* tmB, const void* tmS, const void* tmW, const AttnLayerParams& p, int kind,
                               cudaStream_t s);
 
-// ---- fused FeedForward (gemm_ff.cu): Linear -> GELU -> Linear + residual, hidden activation stays on chip ---------
-struct GemmFFParams {
+// ---- FeedForward chain (gemm_chain.cu): Linear -> GELU -> Linear + residual (+ LayerNorm of the result) in one kernel ---------
+struct FFChainParams {
   int M, C, mid;          // rows, model width, hidden width (mid = C * multiplier)
-  int L, Sb;              // positions per sample; samples per 128-row tile (TMA box of the activation map)
+  int L, Sb;              // positions per sample; samples per 128-row block (TMA box of the activation map)
   const float* b0;        // [mid]
   const float* b2;        // [C]
-  const float* res;       // residual stream [M][C] fp32 (may alias out)
-  float* out;             // [M][C] fp32
-  void* out_op;           // optional operand-dtype copy of out
+  const float* res; int ldres;   // residual: the fp32 token stream (may alias C32)
+  float* C32; int ldc;    // fp32 output
+  void* Cop; int ldcop;   // operand-dtype copy of the output, or LayerNorm(output) when cop_ln (no affine), or null
+  int cop_ln; float ln_eps;
+  void* scratch;          // [SMs][2][128][mid] operand dtype: CTA-private hidden blocks (L2 resident)
+  int rev;                // walk the row blocks from the end (serpentine order)
+  int nst, stage_bytes; unsigned tmem_cols;   // filled by the launcher
 };
-bool gemm_ff_supported(int kind, int C, int mid, int L);
-cudaError_t init_gemm_ff();
-cudaError_t launch_gemm_ff(const void* tmA, const void* tmW0, const void* tmW2, const GemmFFParams& p, int kind, cudaStream_t s);
+bool ff_chain_supported(int kind, int C, int mid, int L);
+size_t ff_chain_scratch_bytes(int kind, int mid);
+int ff_chain_sms();
+cudaError_t init_ff_chain();
+// tmA: activation map; tmB0: W0 [mid][C] with a (KCH x 128) box; tmS: scratch viewed as [SMs][2 * 128][mid]; tmW: W2 [C][mid], (KCH x C) box
+cudaError_t launch_ff_chain(const void* tmA, const void* tmB0, const void* tmS, const void* tmW, const FFChainParams& p, int kind,
+                            cudaStream_t s);
 
 // ---- tensor-core GEMM (gemm_tc.cu) --------------------------------------------------------------
 // kind: 1 = tf32, 2 = bf16.  Wtc must hold the weights pre-converted by convert_weights_tc().

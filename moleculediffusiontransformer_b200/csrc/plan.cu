@@ -70,7 +70,7 @@ struct Op {
   LnApplyParams la{};
   TmaGemmParams tg{};
   GemmAttnParams gat{};
-  GemmFFParams gff{};
+  FFChainParams ffc{};
   AttnLayerParams al{};
   alignas(64) unsigned char tmA[128];
   alignas(64) unsigned char tmB[128];
@@ -138,6 +138,8 @@ struct mdt_plan {
   float *qkv = nullptr, *att = nullptr, *qc = nullptr, *ff = nullptr, *upy = nullptr;
   float *gn_stats = nullptr, *row_stats = nullptr;
   void* attn_scratch = nullptr;   // CTA-private head-output slots of the fused attention-layer kernel (gemm_attn_layer.cu)
+  void* ff_scratch = nullptr;     // CTA-private hidden blocks of the FeedForward chain kernel (gemm_chain.cu)
+  size_t ff_scratch_mid = 0;
   // time path
   float *t_calls = nullptr, *t_feat = nullptr, *t_a = nullptr, *t_b = nullptr, *t_map = nullptr;
   const float *w_time_freq = nullptr, *w_time = nullptr, *b_time = nullptr, *w_map0 = nullptr, *b_map0 = nullptr,
@@ -152,6 +154,9 @@ struct mdt_plan {
   RunParams* d_run = nullptr;      // seed / first sample index / injected-noise base / guidance scale of the running chunk (captured kernels read it)
   cudaEvent_t staged = nullptr;    // the pinned staging tables of the previous call have been copied to the device
   bool ctx_pre_encoded = false;    // cond_dev holds the encoded embedding [B, n_ctx, F] (XDiffusion_x.sample(embedding=...))
+  int sampler_mode = 0;            // 0: ADPM2 / AEuler rows, 1: KarrasSampler rows (mdt_plan_set_sampler_mode)
+  float init_noise_scale = 0.f;
+  float* daux = nullptr;           // slope of denoiser call A (KarrasSampler)
   int n_ctx_cur = 0;
   // graph cache: key (Bc, n_ctx, cfg, has_step_noise, n_iters, single_call); everything else is device resident
   struct GraphEntry { cudaGraphExec_t exec; long long launches; };
@@ -332,17 +337,21 @@ struct Builder {
     emit(prog, op);
   }
 
-  // fused FeedForward (gemm_ff.cu): x_op -> GELU(x W0^T + b0) W2^T + b2 + res, hidden activation never leaves the SM
-  void emit_gemm_ff(std::vector<Op>& prog, const void* xop, int C, int mid, int L, const float* dW0, const float* b0,
-                    const float* dW2, const float* b2, float* t, void* out_op) {
+  // FeedForward chain (gemm_chain.cu): t = t + b2 + GELU(x_op W0^T + b0) W2^T; the hidden activation goes through CTA-private
+  // L2 scratch; cop receives the raw operand copy of the new t (cop_ln = 0) or LayerNorm(t) for the next attention layer
+  void emit_ff_chain(std::vector<Op>& prog, const void* xop, int C, int mid, int L, const float* dW0, const float* b0,
+                     const float* dW2, const float* b2, float* t, void* cop, int cop_ln) {
     Op op; op.type = OP_GEMM_FF; op.rps = L;
-    GemmFFParams& g = op.gff;
-    g.M = 0; g.C = C; g.mid = mid; g.L = L; g.Sb = 128 / L; g.b0 = b0; g.b2 = b2; g.res = t; g.out = t; g.out_op = out_op;
+    FFChainParams& g = op.ffc;
+    g.M = 0; g.C = C; g.mid = mid; g.L = L; g.Sb = L >= 128 ? 1 : 128 / L; g.b0 = b0; g.b2 = b2;
+    g.res = t; g.ldres = C; g.C32 = t; g.ldc = C; g.Cop = cop; g.ldcop = C; g.cop_ln = cop_ln; g.ln_eps = 1e-5f;
+    g.scratch = pl.ff_scratch;   // sized in build() for the widest hidden layer
     const void* w0 = tc_copy(dW0, (size_t)mid * C);
     const void* w2 = tc_copy(dW2, (size_t)C * mid);
     if (make_tmap_act(op.tmA, xop, pl.prec, C, L, (long long)pl.Beff_max) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(ff activation) failed");
-    if (make_tmap_weight(op.tmB, w0, pl.prec, (long long)C, mid, 64) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(ff W0) failed");
-    if (make_tmap_weight(op.tmC, w2, pl.prec, (long long)mid, C, C) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(ff W2) failed");
+    if (make_tmap_weight(op.tmB, w0, pl.prec, (long long)C, mid, 128) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(ff W0) failed");
+    if (make_tmap_act(op.tmC, pl.ff_scratch, pl.prec, mid, 2 * 128, (long long)ff_chain_sms()) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(ff scratch) failed");
+    if (make_tmap_weight(op.tmD, w2, pl.prec, (long long)mid, C, C) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(ff W2) failed");
     emit(prog, op);
   }
 
@@ -548,6 +557,7 @@ struct Builder {
     Src ts{t, C, nullptr, 0, 1.f};
     int nblocks = 0;
     while (has(pre + "blocks." + std::to_string(nblocks) + ".attention.to_q.weight")) ++nblocks;
+    bool tn_is_ln = false;   // tn already holds LayerNorm(t) (written by the previous block's FeedForward chain)
     for (int i = 0; i < nblocks; ++i) {
       const std::string bp = pre + "blocks." + std::to_string(i) + ".";
       const bool has_cross = has(bp + "cross_attention.to_q.weight");
@@ -578,11 +588,11 @@ struct Builder {
               }
           d_wr_self = upload(wr);
           d_bq_self = upload(b.data(), Hd);      // q bias only (see gemm_attn.cu)
-          emit_ln_apply(prog, t, C, L, tn);
+          if (!tn_is_ln) emit_ln_apply(prog, t, C, L, tn);
           layer_self = layer_ok(C, L, 0, false);
           if (!layer_self) emit_gemm_attn(prog, tn, C, L, d_wr_self, d_bq_self, 0, -1, nullptr, nullptr);
         } else if (fast) {
-          emit_ln_apply(prog, t, C, L, tn);
+          if (!tn_is_ln) emit_ln_apply(prog, t, C, L, tn);
           emit_gemm_tma(prog, tn, C, L, 1, d_w, d_b, 3 * Hd, 0, nullptr, nullptr, pl.qkv);
         } else {
           row_stats(prog, t, C, L, pl.row_stats);
@@ -695,15 +705,24 @@ struct Builder {
         }
       }
       // ---- feed forward (no norm): Linear -> GELU -> Linear, + residual
+      tn_is_ln = false;
       {
         const float* d_w0 = upload(T(bp + "feed_forward.0.weight", (int64_t)mid * C), (size_t)mid * C);
         const float* d_b0 = upload(T(bp + "feed_forward.0.bias", mid), mid);
         const float* d_w2 = upload(T(bp + "feed_forward.2.weight", (int64_t)C * mid), (size_t)C * mid);
         const float* d_b2 = upload(T(bp + "feed_forward.2.bias", C), C);
-        // The chained FF kernel keeps the hidden activation on chip but serialises the two GEMMs per 128-row block; on B200 it
-        // measured slower (125 us vs 103 us per level-1 layer, profiles/README.md) than two persistent GEMMs, so it is opt-in.
-        if (fast && getenv("MDT_FUSED_FF") && gemm_ff_supported(pl.prec, C, mid, L)) {
-          emit_gemm_ff(prog, tn, C, mid, L, d_w0, d_b0, d_w2, d_b2, t, (i == nblocks - 1) ? (void*)tn : nullptr);
+        // One chained kernel (gemm_chain.cu): the hidden activation goes through CTA-private L2 scratch instead of an HBM round
+        // trip, and its epilogue hands the next block's self-attention its LayerNorm-ed operand (no separate ln_apply pass).
+        // measured (profiles/README.md, B = 4096): level 1 (C = 128) 108 us vs 134 us for the two GEMMs; level 2 (C = 256: 256 row
+        // blocks for 148 SMs, 1 MB of weights re-streamed per block) 91 vs 86 us, so wider layers keep the two-GEMM path by default
+        const char* fmc = getenv("MDT_FF_CHAIN_MAXC");
+        const bool chain = fast && pl.ff_scratch && (size_t)mid <= pl.ff_scratch_mid && !getenv("MDT_NO_FF_CHAIN") &&
+                           C <= (fmc ? atoi(fmc) : 128) && ff_chain_supported(pl.prec, C, mid, L);
+        if (chain) {
+          const bool last = i == nblocks - 1;
+          const bool ln_next = !last && !getenv("MDT_NO_CHAIN_LN");
+          emit_ff_chain(prog, tn, C, mid, L, d_w0, d_b0, d_w2, d_b2, t, (last || ln_next) ? (void*)tn : nullptr, ln_next ? 1 : 0);
+          tn_is_ln = ln_next;
         } else if (fast) {
           emit_gemm_tma(prog, tn, C, L, 1, d_w0, d_b0, mid, 1, nullptr, nullptr, pl.ff);
           // the last block's output is consumed by to_out as a raw operand: write the copy here
@@ -760,18 +779,33 @@ struct Builder {
     const size_t Be = pl.Beff_max;
     pl.qkv = dalloc(Sqkv * Be); pl.att = dalloc(Satt * Be); pl.qc = dalloc(Satt * Be); pl.ff = dalloc(Sff * Be);
     pl.upy = dalloc(Sup * Be);
+    if (pl.prec != MDT_PREC_FP32) {
+      size_t midmax = 0;
+      for (int i = 1; i <= nlev; ++i) midmax = std::max(midmax, (size_t)Cl[i] * c.ff_multiplier);
+      if (midmax >= 256 && midmax <= 2048) {
+        const size_t bytes = ff_chain_scratch_bytes(pl.prec, (int)midmax);
+        pl.ff_scratch = dalloc((bytes + 3) / 4);
+        pl.ff_scratch_mid = midmax;
+        CK(cudaMemset(pl.ff_scratch, 0, bytes));
+      }
+    }
     pl.gn_stats = dalloc((size_t)2 * 64 * Be);
     pl.row_stats = dalloc((size_t)2 * Lmax * Be);
     pl.xin = dalloc((size_t)c.length * c.in_channels * Be);
     pl.net_out = dalloc((size_t)c.length * c.out_channels * Be);
     pl.x = dalloc((size_t)c.length * c.in_channels * pl.Bmax);
     pl.xmid = dalloc((size_t)c.length * c.in_channels * pl.Bmax);
-    pl.emb = dalloc((size_t)pl.Bmax * c.ctx_max_length * pl.F);
-    pl.emb_stats = dalloc((size_t)pl.Bmax * c.ctx_max_length * 2);
-    pl.emb_null_stats = dalloc((size_t)c.ctx_max_length * 2);
+    pl.daux = dalloc((size_t)c.length * c.in_channels * pl.Bmax);
+    const bool has_ctx = pl.F > 0;   // XUNet1d(type='base'): no conditioning embedding at all
+    if (has_ctx) {
+      pl.emb = dalloc((size_t)pl.Bmax * c.ctx_max_length * pl.F);
+      pl.emb_stats = dalloc((size_t)pl.Bmax * c.ctx_max_length * 2);
+      pl.emb_null_stats = dalloc((size_t)c.ctx_max_length * 2);
+    }
     if (c.resnet_groups > 32) raise(MDT_ERR_INVALID, "resnet_groups > 32 unsupported");
 
     // ---- conditioning encoder + time path weights
+    if (has_ctx) {
     pl.w_fc1 = upload(T("fc1.weight", c.text_embed_dim), c.text_embed_dim);
     pl.b_fc1 = upload(T("fc1.bias", c.text_embed_dim), c.text_embed_dim);
     if (c.pos_emb_fourier) {
@@ -787,6 +821,7 @@ struct Builder {
     if (expectF != pl.F) raise(MDT_ERR_INVALID, "ctx_features %d != encoder width %d", pl.F, expectF);
     pl.w_null_emb = upload(T("unet.fixed_embedding.embedding.weight", (int64_t)c.ctx_max_length * pl.F),
                            (size_t)c.ctx_max_length * pl.F);
+    }
     const int Mf = c.mapping_features, half = c.channels / 2;
     pl.w_time_freq = upload(T("unet.to_time.0.0.weights", half), half);
     pl.w_time = upload(T("unet.to_time.0.1.weight", (int64_t)Mf * (c.channels + 1)), (size_t)Mf * (c.channels + 1));
@@ -986,7 +1021,7 @@ static std::string describe(const Op& op, int Beff) {
     case OP_GEMM: snprintf(b, sizeof b, "gemm      M=%d N=%d K=%d taps=%d stride=%d%s", Beff * op.rps, op.g.N, op.g.K, op.g.a.taps, op.g.a.stride, h); break;
     case OP_GN_APPLY: snprintf(b, sizeof b, "gn_apply  B=%d L=%d C=%d%s%s", Beff, op.ga.L, op.ga.c0 + op.ga.c1, op.ga.raw ? " +raw" : "", h); break;
     case OP_LN_APPLY: snprintf(b, sizeof b, "ln_apply  rows=%d C=%d%s", Beff * op.rps, op.la.C, h); break;
-    case OP_GEMM_FF: snprintf(b, sizeof b, "gemm_ff   M=%d C=%d mid=%d%s", Beff * op.rps, op.gff.C, op.gff.mid, h); break;
+    case OP_GEMM_FF: snprintf(b, sizeof b, "ff_chain  M=%d C=%d mid=%d%s%s", Beff * op.rps, op.ffc.C, op.ffc.mid, op.ffc.cop_ln ? " +ln" : (op.ffc.Cop ? " +cop" : ""), h); break;
     default: snprintf(b, sizeof b, "other(type %d)%s", (int)op.type, h); break;
   }
   return b;
@@ -1019,7 +1054,7 @@ static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_con
     Beff = op.half ? n_cond : Beff_full;
     if (timed) CK(cudaEventRecord(ev0, s));
     const bool streams = op.type == OP_GEMM_TMA || op.type == OP_GEMM_ATTN || op.type == OP_GN_APPLY || op.type == OP_LN_APPLY ||
-                         op.type == OP_ATTN_LAYER;
+                         op.type == OP_ATTN_LAYER || op.type == OP_GEMM_FF;
     rev = (serp && streams) ? (rev ^ 1) : 0;
     switch (op.type) {
       case OP_DUP_ROWS: {
@@ -1052,7 +1087,10 @@ static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_con
         CK(launch_attn_layer(op.tmA, op.tmB, op.tmC, op.tmD, y, pl.prec, s));
         pl.launches++; break;
       }
-      case OP_GEMM_FF: { GemmFFParams g = op.gff; g.M = Beff * op.rps; CK(launch_gemm_ff(op.tmA, op.tmB, op.tmC, g, pl.prec, s)); pl.launches++; break; }
+      case OP_GEMM_FF: {
+        FFChainParams g = op.ffc; g.M = Beff * op.rps; g.rev = rev;
+        CK(launch_ff_chain(op.tmA, op.tmB, op.tmC, op.tmD, g, pl.prec, s)); pl.launches++; break;
+      }
       case OP_GEMM_TMA: { TmaGemmParams g = op.tg; g.M = Beff * op.rps; g.rev = rev; CK(launch_gemm_tma(op.tmA, op.tmB, g, pl.prec, s)); pl.launches++; break; }
       case OP_UPGATHER: CK(launch_upsample_gather(op.in0, op.in1, op.in2, op.out, Beff, op.i0, op.i1, op.i2, s)); pl.launches++; break;
       case OP_PERMUTE: CK(launch_patch_permute(op.in0, op.out, Beff, op.i0, op.i1, op.i2, op.i3, s)); pl.launches++; break;
@@ -1104,6 +1142,7 @@ static void run_time_tables(mdt_plan& pl, int rows, cudaStream_t s) {
 // conditioning embedding -> per-layer cross-attention K/V (loop invariant)
 static void run_context(mdt_plan& pl, const float* cond_dev, int Bc, int n_ctx, bool cfg, cudaStream_t s) {
   const mdt_config& c = pl.cfg;
+  if (pl.F == 0) return;   // unconditional UNet
   const int F = pl.F, Hd = pl.Hd;
   if (pl.ctx_pre_encoded)   // the caller hands over the embedding the wrapper would have computed (generative.py:838-850)
     CK(cudaMemcpyAsync(pl.emb, cond_dev, (size_t)Bc * n_ctx * F * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -1240,7 +1279,7 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
     CK(init_gemm_attn());
     CK(init_gemm_attn_umma());
     CK(init_attn_layer());
-    CK(init_gemm_ff());
+    CK(init_ff_chain());
     pl->cfg = *cfg; pl->device = device; pl->prec = cfg->precision;
     pl->P = cfg->in_channels; pl->L0 = cfg->length; pl->Hd = cfg->heads * cfg->head_features; pl->F = cfg->ctx_features;
     pl->Bmax = cfg->max_batch; pl->Beff_max = 2 * cfg->max_batch;
@@ -1304,6 +1343,14 @@ void mdt_plan_destroy(mdt_plan* pl) {
 int64_t mdt_plan_device_bytes(const mdt_plan* pl) { return pl ? (int64_t)(pl->wcap + pl->act_bytes) : 0; }
 int64_t mdt_plan_launch_count(const mdt_plan* pl) { return pl ? pl->launches : 0; }
 
+int mdt_plan_set_sampler_mode(mdt_plan* pl, int mode, float init_noise_scale) {
+  if (!pl) return fail(MDT_ERR_INVALID, "null plan");
+  if (mode != 0 && mode != 1) return fail(MDT_ERR_INVALID, "unknown sampler mode %d", mode);
+  pl->sampler_mode = mode;
+  pl->init_noise_scale = init_noise_scale;
+  return 0;
+}
+
 int mdt_plan_set_context_mode(mdt_plan* pl, int pre_encoded) {
   if (!pl) return fail(MDT_ERR_INVALID, "null plan");
   pl->ctx_pre_encoded = pre_encoded != 0;
@@ -1330,6 +1377,7 @@ int64_t mdt_plan_read_tap(mdt_plan* pl, const char* name, float* host_dst, int64
 }
 
 static int check_ctx(mdt_plan* pl, int n_ctx) {
+  if (pl->F == 0) return 0;   // XUNet1d(type='base'): the conditioning is ignored (generative.py:862-868)
   if (n_ctx < 1 || n_ctx > pl->cfg.ctx_max_length)
     return fail(MDT_ERR_INVALID, "Input sequence length must be <= max_length (%d > %d)", n_ctx, pl->cfg.ctx_max_length);
   return 0;
@@ -1343,7 +1391,7 @@ int mdt_plan_unet_forward(mdt_plan* pl, const float* x_dev, float time, const fl
   cudaStream_t s = (cudaStream_t)stream;
   try {
     CK(cudaSetDevice(pl->device));
-    const bool cfg = cond_scale != 1.0f;
+    const bool cfg = cond_scale != 1.0f && pl->F > 0;   // classifier-free guidance needs a conditioning embedding
     const int Bc = (int)B, Beff = cfg ? 2 * Bc : Bc;
     CK(cudaEventSynchronize(pl->staged));
     pl->h_tcalls[0] = time;
@@ -1403,7 +1451,7 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
   static_assert(sizeof(IterScalars) == sizeof(mdt_iter_scalars), "scalar layout mismatch");
   try {
     CK(cudaSetDevice(pl->device));
-    const bool cfg = cond_scale != 1.0f;
+    const bool cfg = cond_scale != 1.0f && pl->F > 0;   // classifier-free guidance needs a conditioning embedding
     const int P = pl->P, L = pl->L0;
     const size_t per = (size_t)P * L;
     // a previous call's async copies out of the pinned staging buffers must have drained (only those two copies: the
@@ -1413,6 +1461,8 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
     for (int i = 0; i < n_iters; ++i) { pl->h_tcalls[2 * i] = iters[i].c_noise_a; pl->h_tcalls[2 * i + 1] = iters[i].c_noise_b; }
     bool single_call = true;   // first-order rows (see run_iteration)
     for (int i = 0; i < n_iters; ++i) single_call = single_call && iters[i].dt_mid == 0.0f && iters[i].sigma_mid == iters[i].sigma;
+    const bool karras = pl->sampler_mode == 1;
+    if (karras) single_call = false;
     CK(cudaMemcpyAsync(pl->d_iters, pl->h_iters, sizeof(IterScalars) * n_iters, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(pl->t_calls, pl->h_tcalls, sizeof(float) * 2 * n_iters, cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(pl->staged, s));
@@ -1425,6 +1475,11 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
                           sample_offset + (uint64_t)b0, Bc, P, L, cfg ? 1 : 0, s));
       CK(launch_set_int(pl->d_call, 0, s));
       pl->launches += 2;
+      if (karras) {   // x_hat of step 0: the first step noise goes in ahead of the first denoiser call (diffusion.py:425-426)
+        CK(launch_karras_prenoise(pl->x, pl->xin, step_noise_dev ? step_noise_dev + (size_t)b0 * per : nullptr, pl->init_noise_scale,
+                                  iters[0].c_in_a, seed, sample_offset + (uint64_t)b0, Bc, P, L, cfg ? 1 : 0, s));
+        pl->launches++;
+      }
       StepParams sp{};
       sp.iters = pl->d_iters; sp.call_idx = pl->d_call; sp.net = pl->net_out; sp.x = pl->x; sp.xmid = pl->xmid; sp.xin = pl->xin;
       sp.noise = step_noise_dev ? step_noise_dev + (size_t)b0 * per : nullptr;
@@ -1436,9 +1491,10 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
       rp.noise_iter_stride = sp.noise_iter_stride; rp.cond_scale = cond_scale;
       CK(launch_set_run_params(pl->d_run, rp, s));
       sp.B = Bc; sp.P = P; sp.L = L; sp.n_iters = n_iters; sp.noise_stream = -1; sp.out = nullptr; sp.tokens = nullptr; sp.clamp = clamp;
+      sp.karras = karras ? 1 : 0; sp.daux = pl->daux;
       if (pl->use_graph && !pl->taps_on) {
         // one captured iteration, replayed n_iters times; all per-iteration data is device resident
-        std::vector<long long> key = {Bc, n_ctx, cfg ? 1 : 0, sp.noise ? 1 : 0, (long long)n_iters, single_call ? 1 : 0};
+        std::vector<long long> key = {Bc, n_ctx, cfg ? 1 : 0, sp.noise ? 1 : 0, (long long)n_iters, single_call ? 1 : 0, karras ? 1 : 0};
         auto it = pl->graphs.find(key);
         if (it == pl->graphs.end()) {
           if (pl->graphs.size() > 16) { for (auto& kv : pl->graphs) cudaGraphExecDestroy(kv.second.exec); pl->graphs.clear(); }
@@ -1487,7 +1543,7 @@ int mdt_plan_inpaint(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const f
   cudaStream_t s = (cudaStream_t)stream;
   try {
     CK(cudaSetDevice(pl->device));
-    const bool cfg = cond_scale != 1.0f;
+    const bool cfg = cond_scale != 1.0f && pl->F > 0;   // classifier-free guidance needs a conditioning embedding
     const int P = pl->P, L = pl->L0, R = num_resamples;
     const size_t per = (size_t)P * L;
     const long long draws_per_iter = 2LL * R;              // source noise + R step noises + (R - 1) re-noises

@@ -67,6 +67,26 @@ class AEulerSampler:
         return sigma_up, sigma_down
 
 
+class KarrasSampler:
+    """Stochastic second-order sampler description (diffusion.py:399-453, "algorithm 2" of arXiv:2206.00364 as the reference
+    wrote it): per step  sigma_hat = sigma (1 + gamma),  x_hat = x + sqrt(sigma_hat^2 - sigma^2) s_noise eps,
+    d = (x_hat - D(x_hat, sigma_hat)) / sigma_hat,  x' = x_hat + (sigma_next - sigma_hat) d,
+    d' = (x' - D(x', sigma_next)) / sigma_next,  x_next = x_hat + 0.5 (sigma - sigma_hat) (d + d')   (diffusion.py:433; the step of
+    the correction is zero when s_churn = 0, so a deterministic run returns sigma_0 * noise -- reproduced as is).
+
+    On the device it is an ADPM2-shaped iteration (two denoiser calls) whose second update combines both slopes and whose noise
+    is injected ahead of the first call: mdt_plan_set_sampler_mode(plan, 1, ...)."""
+
+    diffusion_aliases = ("k", "vk")
+
+    def __init__(self, s_tmin: float = 0, s_tmax: float = float("inf"), s_churn: float = 0.0, s_noise: float = 1.0):
+        self.s_tmin, self.s_tmax, self.s_churn, self.s_noise = s_tmin, s_tmax, s_churn, s_noise
+
+    def gammas(self, sigmas: torch.Tensor, num_steps: int) -> torch.Tensor:
+        return torch.where((sigmas >= self.s_tmin) & (sigmas <= self.s_tmax),
+                           min(self.s_churn / num_steps, sqrt(2) - 1), 0.0)          # diffusion.py:441-445
+
+
 # One row per denoiser call / per ADPM2 iteration.  Layout shared with include/mdt_b200.h
 # (struct mdt_iter_scalars): 2 x {c_in, c_noise, c_skip, c_out, inv-free sigma divisor} + update coefficients.
 ITER_SCALAR_FIELDS = (
@@ -87,10 +107,34 @@ def _scale_weights(sigma: torch.Tensor, sigma_data: float):
     return float(c_in), float(c_noise), float(c_skip), float(c_out)
 
 
+def karras_noise_scales(sigmas: torch.Tensor, num_steps: int, sampler: "KarrasSampler") -> List[float]:
+    """sqrt(sigma_hat^2 - sigma^2) * s_noise of every step (diffusion.py:425-426): math.sqrt of a float32 0-dim tensor."""
+    sigmas = sigmas.detach().to("cpu", torch.float32)
+    gammas = sampler.gammas(sigmas, num_steps)
+    out = []
+    for i in range(num_steps - 1):
+        sigma_hat = sigmas[i] + gammas[i] * sigmas[i]
+        out.append(float(torch.ones((), dtype=torch.float32) * sqrt(sigma_hat ** 2 - sigmas[i] ** 2)) * float(sampler.s_noise))
+    return out
+
+
 def build_iter_scalars(sigmas: torch.Tensor, num_steps: int, sampler, sigma_data: float) -> np.ndarray:
     """Host plan: float32 table [num_steps-1, 13] of every scalar the fused step kernels need."""
     sigmas = sigmas.detach().to("cpu", torch.float32)
     rows: List[List[float]] = []
+    if isinstance(sampler, KarrasSampler):
+        # rows in the ADPM2 layout: call A at sigma_hat, call B at sigma_next, dt_mid = sigma_next - sigma_hat,
+        # dt_down = 0.5 (sigma - sigma_hat) (the factor of d + d'), sigma_up = noise scale of the NEXT step (0 after the last)
+        gammas = sampler.gammas(sigmas, num_steps)
+        scales = karras_noise_scales(sigmas, num_steps, sampler)
+        for i in range(num_steps - 1):
+            sig, sig_next = sigmas[i], sigmas[i + 1]
+            sig_hat = sig + gammas[i] * sig
+            a = _scale_weights(sig_hat, sigma_data)
+            b = _scale_weights(sig_next, sigma_data)
+            rows.append([float(sig_hat), *a, float(sig_next), *b, float(sig_next - sig_hat), float(0.5 * (sig - sig_hat)),
+                         scales[i + 1] if i + 1 < num_steps - 1 else 0.0])
+        return np.asarray(rows, dtype=np.float32).reshape(max(num_steps - 1, 0), len(ITER_SCALAR_FIELDS))
     for i in range(num_steps - 1):
         sig, sig_next = sigmas[i], sigmas[i + 1]
         if isinstance(sampler, AEulerSampler):

@@ -33,12 +33,15 @@ class _FourierPE(nn.Module):
 class _QMBase(nn.Module):
     _default_cond_scale = 1.0
     _unet_kwargs: dict = {}
+    # the 'base' branch of every wrapper builds the same UNet (generative.py:790-802, 97-109; graphmodel.py:296-308, 464-476)
+    _base_unet_kwargs: dict = dict(patch_size=8, multipliers=[1, 2, 4], factors=[4, 4], num_blocks=[2, 2], attentions=[1, 1],
+                                   attention_heads=8, attention_features=64, attention_multiplier=2, attention_use_rel_pos=False)
 
     def __init__(self, max_length, channels, pred_dim, unet, context_embedding_max_length, unet_type,
                  pos_emb_fourier, pos_emb_fourier_add, text_embed_dim, embed_dim_position):
         super().__init__()
-        if unet_type != "cfg":
-            raise NotImplementedError("only unet_type='cfg' is on the accelerated path (generative.py:862-868 is not)")
+        if unet_type not in ("cfg", "base"):
+            raise NotImplementedError(f"unet_type={unet_type!r}: the reference builds 'cfg' and 'base' only (generative.py:757-810)")
         self.unet_type = unet_type
         self.fc1 = nn.Linear(1, text_embed_dim)
         self.text_embed_dim = text_embed_dim
@@ -54,13 +57,15 @@ class _QMBase(nn.Module):
         self.pred_dim = pred_dim
         if unet is not None:
             if not isinstance(unet, UNetCFG1dParams):
-                raise TypeError("unet= must be a moleculediffusiontransformer_b200 XUNet1d(type='cfg', ...) instance")
+                raise TypeError("unet= must be a moleculediffusiontransformer_b200 XUNet1d(type='cfg' | 'base', ...) instance")
             self.unet = unet
-        else:
+        elif unet_type == "cfg":
             self.unet = XUNet1d(type="cfg", in_channels=pred_dim, channels=channels,
                                 context_embedding_features=ctx_features,
                                 context_embedding_max_length=context_embedding_max_length,
                                 **self._unet_kwargs)
+        else:   # unconditional UNet1d (generative.py:786-802 / 93-109): the conditioning is encoded and then ignored
+            self.unet = XUNet1d(type="base", in_channels=pred_dim, channels=channels, **self._base_unet_kwargs)
         self.diffusion = XDiffusion_x(type="k", net=self.unet, sigma_data=0.1, dynamic_threshold=0.0)
         object.__setattr__(self.diffusion, "_runner", self._run_sampler)
         self._plans = {}
@@ -175,7 +180,7 @@ class _QMBase(nn.Module):
             raise RuntimeError("moleculediffusiontransformer_b200 runs on sm_100a CUDA devices only "
                                f"(got device={device}); there is no CPU path")
         b = sequences.shape[0]
-        if sequences.shape[1] > self.unet.fixed_embedding.max_length:
+        if self.unet_type == "cfg" and sequences.shape[1] > self.unet.fixed_embedding.max_length:
             raise AssertionError("Input sequence length must be <= max_length")  # modules.py:1194-1195
         if b == 0:  # nothing to launch; keep the reference's return contract
             empty = torch.empty((0, self.pred_dim, self.max_length), dtype=torch.float32, device=device)
@@ -203,7 +208,7 @@ class _QMBase(nn.Module):
                                f"(got device={device}); there is no CPU path")
         if inpaint is None or in_paint_mask is None:
             raise ValueError("inpaint and in_paint_mask are required")
-        if sequences.shape[1] > self.unet.fixed_embedding.max_length:
+        if self.unet_type == "cfg" and sequences.shape[1] > self.unet.fixed_embedding.max_length:
             raise AssertionError("Input sequence length must be <= max_length")  # modules.py:1194-1195
         if seed is None and noise is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
@@ -217,6 +222,7 @@ class QMDiffusion(_QMBase):
     """Inverse model: 12 properties -> (pred_dim, max_length) token logits (generative.py:718-914)."""
 
     _default_cond_scale = 7.5
+    _base_unet_kwargs = dict(_QMBase._base_unet_kwargs, pre_transformer=2)      # generative.py:790
     _unet_kwargs = dict(pre_transformer=2, patch_size=1, multipliers=[1, 2, 4], factors=[4, 4],
                         num_blocks=[3, 3], attentions=[4, 4], attention_heads=8, attention_features=64,
                         attention_multiplier=2, attention_use_rel_pos=False)

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from .diffusion import ITER_SCALAR_FIELDS, build_iter_scalars
+from .diffusion import ITER_SCALAR_FIELDS, KarrasSampler, build_iter_scalars, karras_noise_scales
 
 
 def default_precision() -> str:
@@ -46,7 +46,8 @@ def make_config(model, precision: str, max_batch: int, max_timesteps: int) -> _c
     cfg.kernel_multiplier_downsample = u.kernel_multiplier_downsample
     cfg.use_skip_scale = int(u.use_skip_scale)
     cfg.mapping_features = u.mapping_features
-    cfg.ctx_features, cfg.ctx_max_length = u.context_embedding_features, u.context_embedding_max_length
+    # XUNet1d(type='base') takes no conditioning: ctx_features = 0 switches the encoder, cross-attention and guidance off
+    cfg.ctx_features, cfg.ctx_max_length = u.context_embedding_features or 0, u.context_embedding_max_length or 0
     cfg.text_embed_dim, cfg.embed_dim_position = model.text_embed_dim, model.embed_dim_position
     cfg.pos_emb_fourier, cfg.pos_emb_fourier_add = int(model.pos_emb_fourier), int(model.pos_emb_fourier_add)
     cfg.sigma_data = model.diffusion.diffusion.sigma_data
@@ -82,7 +83,7 @@ class SamplerPlan:
         with torch.cuda.device(self.device):   # plan creation must not move the process's current device
             _capi.check(self.lib.mdt_plan_create(C.byref(self.cfg), arr, len(sd), self.index, C.byref(handle)))
         self.handle = handle
-        self.ctx_features = model.unet.cfg.context_embedding_features
+        self.ctx_features = model.unet.cfg.context_embedding_features or 0
         self.weights_version = None
 
     # ------------------------------------------------------------------
@@ -123,6 +124,8 @@ class SamplerPlan:
         """`sequences` is the raw conditioning [B, n] or, with ``pre_encoded``, the encoded embedding [B, n, F]."""
         if num_steps > self.max_timesteps:
             raise ValueError(f"timesteps={num_steps} exceeds this plan's max_timesteps={self.max_timesteps}")
+        if self.ctx_features == 0:     # unconditional UNet: `sequences` only carries the batch size (generative.py:862-868)
+            sequences, pre_encoded, cond_scale = torch.zeros((sequences.shape[0], 1)), False, 1.0
         if pre_encoded:
             if sequences.dim() != 3 or sequences.shape[2] != self.ctx_features:
                 raise ValueError(f"embedding must have shape [B, n, {self.ctx_features}]")
@@ -146,6 +149,11 @@ class SamplerPlan:
             out = torch.empty((b, P, L), dtype=torch.float32, device=self.device)
             tokens = torch.empty((b, L), dtype=torch.uint8, device=self.device) if return_tokens else None
             _capi.check(self.lib.mdt_plan_set_context_mode(self.handle, int(bool(pre_encoded))))
+            if isinstance(sampler, KarrasSampler):
+                s0 = karras_noise_scales(sigma_schedule(num_steps, "cpu"), num_steps, sampler)[0]
+                _capi.check(self.lib.mdt_plan_set_sampler_mode(self.handle, 1, float(s0)))
+            else:
+                _capi.check(self.lib.mdt_plan_set_sampler_mode(self.handle, 0, 0.0))
             _capi.check(self.lib.mdt_plan_sample(
                 self.handle, cond.data_ptr(), n_ctx, n0.data_ptr() if n0 is not None else None,
                 sn.data_ptr() if sn is not None else None, table.ctypes.data, table.shape[0],

@@ -41,8 +41,8 @@ class UNetConfig:
     use_skip_scale: bool = True
     out_channels: Optional[int] = None
     context_features_multiplier: int = 4
-    context_embedding_features: int = 128
-    context_embedding_max_length: int = 12
+    context_embedding_features: Optional[int] = 128     # None: unconditional UNet1d (type='base'), no cross-attention
+    context_embedding_max_length: Optional[int] = 12
     pre_transformer: int = 0
     attention_heads: int = 8
     attention_features: int = 64
@@ -212,14 +212,28 @@ class UNetCFG1dParams(_Holder):
         to_out.block = _resnet(c * mult[0] // cfg.patch_size, cfg.out_channels, 1, m)
         self.to_out = to_out
 
-        fe = _Holder()
-        fe.max_length = cfg.context_embedding_max_length
-        fe.embedding = nn.Embedding(cfg.context_embedding_max_length, ctx)
-        self.fixed_embedding = fe
+        if ctx:   # UNetCFG1d only (modules.py:1215-1226): the learned null embedding of classifier-free guidance
+            fe = _Holder()
+            fe.max_length = cfg.context_embedding_max_length
+            fe.embedding = nn.Embedding(cfg.context_embedding_max_length, ctx)
+            self.fixed_embedding = fe
+
+
+class UNet1dParams(UNetCFG1dParams):
+    """Parameters of the plain ``UNet1d`` (modules.py:934-1098; ``XUNet1d(type='base')``): same construction order, no
+    conditioning embedding, hence no cross-attention layers and no ``fixed_embedding``."""
+
+    def __init__(self, cfg: UNetConfig):
+        assert not cfg.context_embedding_features, "type='base' takes no context_embedding_features (modules.py:1316-1326)"
+        super().__init__(cfg)
 
 
 def XUNet1d(type: str = "cfg", **kwargs) -> UNetCFG1dParams:
-    """Factory with the reference's signature (modules.py:1316-1326); only ``type='cfg'`` is on the path."""
-    if type != "cfg":
-        raise NotImplementedError(f"unet type {type!r} is outside the accelerated path (only 'cfg')")
-    return UNetCFG1dParams(UNetConfig(**kwargs))
+    """Factory with the reference's signature (modules.py:1316-1326): ``type='cfg'`` (UNetCFG1d) or ``'base'`` (UNet1d)."""
+    if type == "cfg":
+        return UNetCFG1dParams(UNetConfig(**kwargs))
+    if type == "base":
+        kwargs.setdefault("context_embedding_features", None)
+        kwargs.setdefault("context_embedding_max_length", None)
+        return UNet1dParams(UNetConfig(**kwargs))
+    raise NotImplementedError(f"unet type {type!r} is outside the accelerated path ('cfg' and 'base' only)")

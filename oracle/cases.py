@@ -12,6 +12,15 @@ WIDE = dict(max_length=128, pred_dim=32, channels=128, unet_type="cfg", context_
 PAPER = dict(max_length=32, pred_dim=22, channels=128, unet_type="cfg", context_embedding_max_length=12,
              pos_emb_fourier=True, pos_emb_fourier_add=False, text_embed_dim=64, embed_dim_position=64)
 
+# sibling wrappers / UNet types on the same executor: unet_type='base' (generative.py:786-810, 93-117; patch_size 8, so
+# lengths >= 128) and the graphmodel.py wrappers AnalogDiffusionSparse (patch 8) / AnalogDiffusionFull (patch 4)
+BASE_INV = dict(INV64, max_length=128, unet_type="base")
+BASE_FWD = dict(FWD64, max_length=128, unet_type="base")
+ANALOG_SPARSE = dict(max_length=128, pred_dim=3, channels=64, unet_type="cfg", context_embedding_max_length=12,
+                     pos_emb_fourier=True, pos_emb_fourier_add=False, text_embed_dim=64, embed_dim_position=64)
+ANALOG_FULL = dict(max_length=64, pred_dim=8, channels=64, unet_type="cfg", context_embedding_max_length=12,
+                   pos_emb_fourier=True, pos_emb_fourier_add=False, text_embed_dim=64, embed_dim_position=64)
+
 # name -> (kind, ctor kwargs, model seed, data seed, batch, ctx_len, cond_scale, timesteps, clamp)
 CASES = {
     "inv64_cs1":    ("inverse", INV64, 0, 1234, 4, 12, 1.0, 64, False),
@@ -21,6 +30,12 @@ CASES = {
     "fwd64_cs2":    ("forward", FWD64, 0, 2, 2, 64, 2.0, 6, False),
     "wide_cs7p5":   ("inverse", WIDE, 0, 3, 2, 12, 7.5, 6, False),
     "paper_cs2":    ("inverse", PAPER, 0, 5, 2, 12, 2.0, 6, False),
+    # BASELINE.json configs[3] at its real depth: 128 timesteps = 254 denoiser calls x 2 branches for rounding error to accumulate over
+    "wide_cs7p5_t128": ("inverse", WIDE, 0, 31, 4, 12, 7.5, 128, False),
+    "base128_inv":  ("inverse", BASE_INV, 0, 51, 3, 12, 7.5, 6, False),        # cond_scale is ignored by the 'base' branch
+    "base128_fwd":  ("forward", BASE_FWD, 0, 52, 2, 64, 1.0, 6, True),
+    "analog_sparse": ("analog_sparse", ANALOG_SPARSE, 0, 53, 3, 12, 2.0, 6, False),
+    "analog_full":  ("analog_full", ANALOG_FULL, 0, 54, 2, 9, 7.5, 6, False),
 }
 
 

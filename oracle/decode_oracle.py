@@ -8,8 +8,10 @@ Follows ``reverse_tokenize`` (MoleculeDiffusion/generative.py:1069-1078):
 ``tokenizer_X`` is a Keras ``Tokenizer`` (tensorflow.keras.preprocessing.text, not installed here and not vendored by the
 reference; Keras 2.x ``Tokenizer.sequences_to_texts_generator``): for every id of a row it looks the id up in ``index_word``;
 ids without an entry are skipped unless an ``oov_token`` was configured (the notebooks configure none), and the words found are
-joined with ' '.  PARITY UNPINNED for this helper: there is no Keras here to run and the reference has no test or fixture for it;
-the restatement is pinned only to the published behaviour above.
+joined with ' '.  Keras itself is not installed here, so the pin is the reference's own recorded evidence: the tokenizer
+vocabulary, six (token row, ``reverse_tokenize`` output) pairs and eight decoded SMILES strings that the authors' run of
+``Inverse_Diffusion.ipynb`` left in its cell outputs (cells 36, 38, 65), extracted by ``oracle/make_decode_fixture.py`` into
+``tests/golden/decode_notebook.json`` and checked in ``tests/test_host_cpu.py::test_decode_oracle_against_notebook_record``.
 """
 from typing import Dict, List, Sequence
 

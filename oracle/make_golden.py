@@ -30,7 +30,8 @@ def main(names=None):
             models[key] = rl.build_model(kind, seed=mseed, **kw)
         m = models[key]
         seq, noise0, step_noise = make_inputs(name)
-        with rl.injected_noise(noise0, step_noise):
+        import contextlib, io
+        with rl.injected_noise(noise0, step_noise), contextlib.redirect_stdout(io.StringIO()):
             out = m.sample(seq, "cpu", cond_scale=cs, timesteps=steps, clamp=clamp)
         # one raw UNet evaluation (conditional branch) at sigma = 1.0 for kernel-level parity
         with torch.no_grad():
@@ -38,7 +39,7 @@ def main(names=None):
             emb = m.GELUact(m.fc1(x))
             emb = torch.cat((emb, m.p_enc_1d(emb)), 2)
             t = torch.full((b,), 0.37)
-            net = m.unet(noise0, t, embedding=emb, embedding_scale=cs)
+            net = m.unet(noise0, t) if kw.get("unet_type") == "base" else m.unet(noise0, t, embedding=emb, embedding_scale=cs)
         pcount = sum(p.numel() for p in m.unet.parameters()) + m.fc1.weight.numel() + m.fc1.bias.numel()
         psum = float(sum(p.double().sum() for p in {id(p): p for p in m.parameters()}.values()))
         np.savez_compressed(
@@ -84,8 +85,39 @@ def main_aeuler():
         print(f"aeuler_{name}: out.sum={out.double().sum():.6f} draws={st['i']}")
 
 
+# name of the ADPM2 case whose model / inputs are reused -> KarrasSampler kwargs (diffusion.py:404-415)
+KARRAS_CASES = {
+    "inv64_short_ctx_clamp": dict(s_churn=40.0),                                       # gamma capped at sqrt(2) - 1 on every step
+    "inv64_cs7p5": dict(s_churn=10.0, s_tmin=0.05, s_tmax=5.0, s_noise=1.0),           # gamma = 10 / 64 inside the window, 0 outside
+}
+
+
+def main_karras():
+    """model.diffusion.sample(noise, sampler=KarrasSampler(s_churn > 0, ...), ...) through the reference's injection point, every
+    randn_like injected (one draw per step, diffusion.py:425)."""
+    rl.load()
+    import MoleculeDiffusion.diffusion as rd
+
+    for name, skw in KARRAS_CASES.items():
+        kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES[name]
+        m = rl.build_model(kind, seed=mseed, **kw)
+        seq, noise0, step_noise = make_inputs(name)
+        with torch.no_grad():
+            x = seq.float().unsqueeze(2)
+            emb = m.GELUact(m.fc1(x))
+            emb = torch.cat((emb, m.p_enc_1d(emb)), 2)
+        with rl.injected_noise(noise0, step_noise) as st:
+            out = m.diffusion.sample(noise0, embedding=emb, embedding_scale=cs, num_steps=steps, sampler=rd.KarrasSampler(**skw),
+                                     sigma_schedule=rd.KarrasSchedule(sigma_min=0.001, sigma_max=9.0, rho=3.0), clamp=clamp)
+        assert st["i"] == steps - 1, (st["i"], steps)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"karras_{name}.npz"), out=out.numpy())
+        print(f"karras_{name}: out.sum={out.double().sum():.6f} draws={st['i']}")
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["inpaint"]:
+    if sys.argv[1:] == ["karras"]:
+        main_karras()
+    elif sys.argv[1:] == ["inpaint"]:
         main_inpaint()
     elif sys.argv[1:] == ["aeuler"]:
         main_aeuler()

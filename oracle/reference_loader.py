@@ -139,6 +139,9 @@ def build_model(kind: str, seed: int = 0, **kw):
             m = gen.QMDiffusion(**kw)
         elif kind == "forward":
             m = gen.QMDiffusionForward(**kw)
+        elif kind in ("analog_sparse", "analog_full"):
+            gm = importlib.import_module("MoleculeDiffusion.graphmodel")
+            m = (gm.AnalogDiffusionSparse if kind == "analog_sparse" else gm.AnalogDiffusionFull)(**kw)
         else:
             raise ValueError(kind)
     return m.eval()

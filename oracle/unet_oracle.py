@@ -180,7 +180,10 @@ def unet_forward(sd: SD, cfg: dict, x: Tensor, time: Tensor, embedding: Tensor, 
 
 def unet_cfg_forward(sd: SD, cfg: dict, x: Tensor, time: Tensor, embedding: Tensor, embedding_scale: float,
                      p: str = "unet.") -> Tensor:
-    """UNetCFG1d.forward (modules.py:1228-1255)."""
+    """UNetCFG1d.forward (modules.py:1228-1255); a state_dict without ``fixed_embedding`` is the plain UNet1d of
+    ``XUNet1d(type='base')`` (modules.py:1144-1180), which the wrappers call without any conditioning (generative.py:862-868)."""
+    if (p + "fixed_embedding.embedding.weight") not in sd:
+        return unet_forward(sd, cfg, x, time, None, p)
     if embedding_scale != 1.0:
         n = embedding.shape[1]
         fixed = sd[p + "fixed_embedding.embedding.weight"][:n][None].expand(embedding.shape[0], -1, -1)
@@ -256,6 +259,27 @@ def aeuler_sample(fn: Callable, noise: Tensor, sigmas: Tensor, num_steps: int, s
     return x
 
 
+def karras_sample(fn: Callable, noise: Tensor, sigmas: Tensor, num_steps: int, step_noise, s_tmin: float = 0.0,
+                  s_tmax: float = float("inf"), s_churn: float = 0.0, s_noise: float = 1.0) -> Tensor:
+    """KarrasSampler.forward/step (diffusion.py:399-453) exactly as written there -- including the second-order correction
+    ``x_hat + 0.5 * (sigma - sigma_hat) * (d + d_prime)`` (diffusion.py:433), whose step is zero when s_churn = 0;
+    ``step_noise[i]`` replaces the randn_like of step i."""
+    x = sigmas[0] * noise
+    gammas = torch.where((sigmas >= s_tmin) & (sigmas <= s_tmax), min(s_churn / num_steps, math.sqrt(2) - 1), 0.0)
+    for i in range(num_steps - 1):
+        sigma, sigma_next, gamma = sigmas[i], sigmas[i + 1], gammas[i]
+        sigma_hat = sigma + gamma * sigma
+        epsilon = s_noise * step_noise[i]
+        x_hat = x + math.sqrt(sigma_hat ** 2 - sigma ** 2) * epsilon
+        d = (x_hat - fn(x_hat, sigma_hat)) / sigma_hat
+        x_next = x_hat + (sigma_next - sigma_hat) * d
+        if sigma_next != 0:
+            d_prime = (x_next - fn(x_next, sigma_next)) / sigma_next
+            x_next = x_hat + 0.5 * (sigma - sigma_hat) * (d + d_prime)
+        x = x_next
+    return x
+
+
 def adpm2_inpaint(fn: Callable, source: Tensor, mask: Tensor, sigmas: Tensor, num_steps: int, num_resamples: int, draws,
                   rho: float = 1.0) -> Tensor:
     """ADPM2Sampler.inpaint (diffusion.py:526-549); ``draws`` replays every randn_like in call order."""
@@ -292,7 +316,8 @@ def inpaint(sd: SD, cfg: dict, sequences: Tensor, source: Tensor, mask: Tensor, 
 
 @torch.no_grad()
 def sample(sd: SD, cfg: dict, sequences: Tensor, noise0: Tensor, step_noise, cond_scale: float, timesteps: int,
-           clamp: bool = False, pos_emb_fourier: bool = True, pos_emb_fourier_add: bool = False, sampler: str = "adpm2") -> Tensor:
+           clamp: bool = False, pos_emb_fourier: bool = True, pos_emb_fourier_add: bool = False, sampler: str = "adpm2",
+           sampler_kwargs: Optional[dict] = None) -> Tensor:
     """QMDiffusion.sample / QMDiffusionForward.sample (generative.py:834-870, 146-180) with injected noise; ``sampler="aeuler"``
     restates ``model.diffusion.sample(..., sampler=AEulerSampler())`` (diffusion.py:724-741, 456-483)."""
     emb = encode_conditioning(sd, sequences, pos_emb_fourier, pos_emb_fourier_add)
@@ -302,6 +327,8 @@ def sample(sd: SD, cfg: dict, sequences: Tensor, noise0: Tensor, step_noise, con
         x = adpm2_sample(fn, noise0, sigmas, timesteps, step_noise)
     elif sampler == "aeuler":
         x = aeuler_sample(fn, noise0, sigmas, timesteps, step_noise)
+    elif sampler == "karras":
+        x = karras_sample(fn, noise0, sigmas, timesteps, step_noise, **(sampler_kwargs or {}))
     else:
         raise ValueError(sampler)
     return x.clamp(-1.0, 1.0) if clamp else x

@@ -32,7 +32,8 @@ def model_cache():
         key = (kind, tuple(sorted(kw.items())), seed)
         if key not in cache:
             torch.manual_seed(seed)
-            cls = mdt.QMDiffusion if kind == "inverse" else mdt.QMDiffusionForward
+            cls = {"inverse": mdt.QMDiffusion, "forward": mdt.QMDiffusionForward, "analog_sparse": mdt.AnalogDiffusionSparse,
+                   "analog_full": mdt.AnalogDiffusionFull}[kind]
             cache[key] = cls(**kw).eval()
         return cache[key]
 

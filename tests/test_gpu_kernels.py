@@ -111,3 +111,22 @@ def test_decode_tokens_matches_reverse_tokenize(shape):
     got = reverse_tokenize(vocab, toks.to("cuda:0"))
     assert got == reverse_tokenize_oracle(vocab, toks.numpy())
     assert reverse_tokenize(vocab, torch.empty((0, l), dtype=torch.uint8, device="cuda:0")) == []
+
+
+def test_decode_tokens_against_notebook_record():
+    """mdt_op_decode_tokens reproduces what the reference's own run of reverse_tokenize printed (Inverse_Diffusion.ipynb cells
+    36 / 38 / 65; tests/golden/decode_notebook.json) -- the reference-held pin for the decode row."""
+    import json
+    import os
+    import numpy as np
+    import moleculediffusiontransformer_b200 as mdt
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rec = json.load(open(os.path.join(root, "tests", "golden", "decode_notebook.json")))
+    index_word = {int(k): v for k, v in rec["index_word"].items()}
+    rows = torch.tensor(rec["tokenized_rows"], dtype=torch.uint8, device="cuda")
+    assert mdt.reverse_tokenize(index_word, rows) == rec["reverse_tokenized"]
+    ids = np.zeros((len(rec["decoded_smiles"]), 64), dtype=np.uint8)
+    for i, smi in enumerate(rec["decoded_smiles"]):
+        ids[i, 1:2 * len(smi):2] = [rec["word_index"][ch] for ch in smi]
+    assert mdt.reverse_tokenize(index_word, torch.from_numpy(ids).cuda()) == rec["decoded_smiles"]

@@ -198,6 +198,32 @@ def test_decode_oracle_follows_keras_sequences_to_texts():
     assert reverse_tokenize(QM9_LIKE_VOCAB, x, 21.0) == ["CCO", "(=", ""]
 
 
+def _decode_record():
+    import json
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "decode_notebook.json")))
+
+
+def test_decode_oracle_against_notebook_record():
+    """The reference-held known answers for reverse_tokenize (generative.py:1069-1078): vocabulary, token rows and the strings the
+    authors' own run printed (Inverse_Diffusion.ipynb cells 36 / 38 / 65, extracted by oracle/make_decode_fixture.py)."""
+    import numpy as np
+    from oracle.decode_oracle import reverse_tokenize
+
+    rec = _decode_record()
+    index_word = {int(k): v for k, v in rec["index_word"].items()}
+    assert {v: k for k, v in index_word.items()} == rec["word_index"] and len(index_word) == 21
+    rows = np.asarray(rec["tokenized_rows"])
+    assert reverse_tokenize(index_word, rows) == rec["reverse_tokenized"]
+    # the call site divides by X_norm_factor first and reverse_tokenize multiplies it back (generative.py:1071, 1207-1229)
+    assert reverse_tokenize(index_word, rows / rec["x_norm_factor"], rec["x_norm_factor"]) == rec["reverse_tokenized"]
+    # strings the reference decoded from sampled tokens: tokenise with the recorded vocabulary, pad with id 0, decode
+    for smi in rec["decoded_smiles"]:
+        ids = [rec["word_index"][ch] for ch in smi] + [0] * (32 - len(smi))
+        assert reverse_tokenize(index_word, np.asarray([ids])) == [smi]
+        scattered = np.zeros(64, dtype=np.int64); scattered[1:2 * len(smi):2] = ids[:len(smi)]   # padding between characters is dropped
+        assert reverse_tokenize(index_word, scattered[None]) == [smi]
+
+
 def test_vocabulary_table_rejects_what_the_device_decoder_cannot_express():
     from moleculediffusiontransformer_b200.screening import is_novel, vocabulary_table
 

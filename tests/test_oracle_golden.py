@@ -7,7 +7,7 @@ from conftest import golden
 from oracle import unet_oracle as orc
 from oracle.cases import CASES, INPAINT_CASES, make_inpaint_inputs, make_inputs
 
-FAST = ["inv64_cs1", "inv64_short_ctx_clamp", "fwd64_cs2", "paper_cs2"]
+FAST = ["inv64_cs1", "inv64_short_ctx_clamp", "fwd64_cs2", "paper_cs2", "base128_inv", "base128_fwd", "analog_sparse", "analog_full"]
 
 
 def _sd_cfg(model):
@@ -91,3 +91,41 @@ def test_aeuler_sampler_matches_reference(name, model_cache):
     assert orc.rel_l2(out, ref) < 1e-5
     assert (orc.tokens_from_logits(out) == orc.tokens_from_logits(ref)).float().mean() == 1.0
     assert orc.rel_l2(out, torch.from_numpy(golden(name)["out"])) > 1e-2        # and it is not the ADPM2 result
+
+
+@pytest.mark.parametrize("name", ["inv64_short_ctx_clamp", "inv64_cs7p5"])
+def test_karras_sampler_matches_reference(name, model_cache):
+    """Oracle restatement of KarrasSampler with s_churn > 0 (diffusion.py:399-453) against fixtures produced by the reference
+    through ``model.diffusion.sample(noise, sampler=KarrasSampler(...), ...)`` (oracle/make_golden.py karras)."""
+    from oracle.make_golden import KARRAS_CASES
+
+    kind, kw, mseed, dseed, b, n, cs, steps, clamp = CASES[name]
+    m = model_cache(kind, kw, mseed)
+    sd, cfg = _sd_cfg(m)
+    seq, noise0, step_noise = make_inputs(name)
+    out = orc.sample(sd, cfg, seq, noise0, step_noise, cs, steps, clamp, sampler="karras", sampler_kwargs=KARRAS_CASES[name])
+    ref = torch.from_numpy(golden("karras_" + name)["out"])
+    assert orc.rel_l2(out, ref) < 1e-5
+    assert orc.rel_l2(out, torch.from_numpy(golden(name)["out"])) > 1e-2        # and it is not the ADPM2 result
+
+
+def test_karras_scalar_rows_follow_the_reference_arithmetic():
+    """Host plan rows for KarrasSampler: sigma_hat, the two coefficient sets, dt_mid, 0.5 (sigma - sigma_hat) and the next step's
+    noise scale, each computed with the reference's float32-tensor / Python-double mix (diffusion.py:422-434, 441-445)."""
+    import math
+    import moleculediffusiontransformer_b200 as mdt
+    from moleculediffusiontransformer_b200.diffusion import karras_noise_scales
+
+    N = 9
+    sig = orc.karras_sigmas(N)
+    smp = mdt.KarrasSampler(s_churn=3.0, s_tmin=0.01, s_tmax=4.0, s_noise=1.0)
+    rows = mdt.build_iter_scalars(sig, N, smp, 0.1)
+    scales = karras_noise_scales(sig, N, smp)
+    gam = torch.where((sig >= 0.01) & (sig <= 4.0), min(3.0 / N, math.sqrt(2) - 1), 0.0)
+    assert rows.shape == (N - 1, 13) and float(gam[0]) == 0.0 and float(gam[3]) > 0
+    for i in range(N - 1):
+        s_hat = sig[i] + gam[i] * sig[i]
+        assert rows[i, 0] == float(s_hat) and rows[i, 5] == float(sig[i + 1])
+        assert rows[i, 10] == float(sig[i + 1] - s_hat) and rows[i, 11] == float(0.5 * (sig[i] - s_hat))
+        assert scales[i] == float(torch.ones(()) * math.sqrt(s_hat ** 2 - sig[i] ** 2))
+        assert rows[i, 12] == (np.float32(scales[i + 1]) if i + 1 < N - 1 else 0.0)
