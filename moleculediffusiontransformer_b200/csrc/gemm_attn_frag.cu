@@ -1,0 +1,496 @@
+// gemm_attn_frag.cu -- second generation of the whole-attention-layer kernel (gemm_attn_layer.cu): same pipelines (per-head
+// projection on tcgen05 -> softmax attention -> out-projection on tcgen05 from CTA-private L2 scratch -> bias + residual), but the
+// attention warps read their mma.sync operand fragments STRAIGHT FROM TMEM:
+//
+//   tcgen05.ld.16x256b delivers 16 accumulator rows x 8 columns per register quad in exactly the mma.m16n8 accumulator layout
+//   (thread (g, q): row g and g + 8, columns 2q and 2q + 1).  With the k index relabelled consistently on both operands
+//   (k = q <-> column 2q, k = q + 4 <-> column 2q + 1) that quad IS the A fragment of q and, read from the key rows, the two B
+//   fragments of k.  So q and k never go through shared memory; only v (whose B fragment is transposed) passes through a
+//   warp-private 16 x 64 tile.  No cross-warp barrier is left in the head loop, the staging shared memory shrinks from 104 KB to
+//   68 KB, and SIXTEEN attention warps (two groups of eight, one per TMEM accumulator) keep two heads in flight.
+//
+// Supported: self-attention with L in {4, 8, 16} (short samples share one block-diagonal m16 tile) and cross-attention on the
+// fragment-ordered K/V cache with L in {4, 8, 16}; everything else stays on gemm_attn_layer.cu.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "attn_math.cuh"
+
+namespace mdt {
+namespace tc {
+
+constexpr int Z_TM = 128;
+constexpr int Z_MAXST = 4;
+constexpr int Z_ABYTES = Z_TM * 128;
+constexpr int Z_EPI_WARPS = 16;
+constexpr int Z_THREADS = 64 + 32 * Z_EPI_WARPS;
+constexpr int Z_VLD = 68;       // warp-private v tile row stride in floats (64 + 4: conflict-free fragment loads)
+constexpr int Z_LA = 2;         // heads of block k + 1 that run ahead of block k's out-projection (scratch slots = heads + Z_LA)
+
+__device__ __forceinline__ void z_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// 16 TMEM lanes x 32 columns -> 16 registers: quad c = columns 8c .. 8c + 7 in the m16n8 accumulator layout (no wait)
+__device__ __forceinline__ void tmem_ld16x256_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// softmax over <= 16 keys held as two m16n8 score tiles (thread: rows g / g + 8, keys 8t + 2q, 8t + 2q + 1); returns the
+// probabilities as tf32 A fragments of P V (key permutation of attn_math.cuh).  bm: block-diagonal mask (~(blk - 1)) or 0.
+__device__ __forceinline__ void softmax_2tiles(float (&sc)[2][4], int nk, float scale, int bm, int g, int q, uint32_t (&pa)[2][4]) {
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int j = t * 8 + 2 * q;
+    const bool in0 = ((j ^ g) & bm) == 0, in1 = ((j ^ (g + 8)) & bm) == 0;
+    sc[t][0] = (j < nk && in0) ? sc[t][0] * scale : -INFINITY;
+    sc[t][1] = (j + 1 < nk && in0) ? sc[t][1] * scale : -INFINITY;
+    sc[t][2] = (j < nk && in1) ? sc[t][2] * scale : -INFINITY;
+    sc[t][3] = (j + 1 < nk && in1) ? sc[t][3] * scale : -INFINITY;
+    m0 = fmaxf(m0, fmaxf(sc[t][0], sc[t][1]));
+    m1 = fmaxf(m1, fmaxf(sc[t][2], sc[t][3]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    sc[t][0] = __expf(sc[t][0] - m0); sc[t][1] = __expf(sc[t][1] - m0);
+    sc[t][2] = __expf(sc[t][2] - m1); sc[t][3] = __expf(sc[t][3] - m1);
+    s0 += sc[t][0] + sc[t][1]; s1 += sc[t][2] + sc[t][3];
+  }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  const float inv0 = 1.0f / s0, inv1 = 1.0f / s1;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    pa[t][0] = to_tf32(sc[t][0] * inv0);   // (row g,     key 8t + 2q)
+    pa[t][1] = to_tf32(sc[t][2] * inv1);   // (row g + 8, key 8t + 2q)
+    pa[t][2] = to_tf32(sc[t][1] * inv0);   // (row g,     key 8t + 2q + 1)
+    pa[t][3] = to_tf32(sc[t][3] * inv1);   // (row g + 8, key 8t + 2q + 1)
+  }
+}
+
+// q fragments (with the folded q bias) for the 16 rows at `tq`: two halves of 32 features each are loaded by the caller
+template <int KIND>
+__device__ __forceinline__ void add_q_bias(uint32_t (&qf)[16], const float* __restrict__ bias32, int q) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float2 b = __ldg(reinterpret_cast<const float2*>(bias32 + 8 * c + 2 * q));
+    qf[4 * c + 0] = __float_as_uint(__uint_as_float(qf[4 * c + 0]) + b.x);
+    qf[4 * c + 1] = __float_as_uint(__uint_as_float(qf[4 * c + 1]) + b.y);
+    qf[4 * c + 2] = __float_as_uint(__uint_as_float(qf[4 * c + 2]) + b.x);
+    qf[4 * c + 3] = __float_as_uint(__uint_as_float(qf[4 * c + 3]) + b.y);
+  }
+}
+
+template <int OK>
+__device__ __forceinline__ void store_o_tiles(const float (&oc)[8][4], void* out, size_t out_base, int ldo, int rows_valid, int g, int q) {
+  typedef SmemIO<OK> OUT;
+  const bool ok0 = g < rows_valid, ok1 = g + 8 < rows_valid;
+  const size_t o0 = out_base + (size_t)g * ldo + 2 * q, o1 = o0 + (size_t)8 * ldo;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    if (ok0) OUT::st2(out, o0 + n * 8, oc[n][0], oc[n][1]);
+    if (ok1) OUT::st2(out, o1 + n * 8, oc[n][2], oc[n][3]);
+  }
+}
+
+// MODE: 0 self (L in {4, 8, 16}: 16 rows = 16 / L samples, block-diagonal mask when L < 16);  3 cross on the fragment-ordered cache
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ CUtensorMap tmS,
+                                                                const __grid_constant__ CUtensorMap tmW,
+                                                                const AttnLayerParams p, const uint32_t idesc,
+                                                                const uint32_t idesc_o) {
+  constexpr int KCH = (KIND == 1) ? 32 : 64;
+  constexpr bool CROSS = MODE >= 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[Z_MAXST];
+  __shared__ __align__(8) uint64_t empty_bar[Z_MAXST];
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
+  __shared__ __align__(8) uint64_t att_ready, out_full, out_empty;
+  __shared__ uint32_t tmem_base_s;
+
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const GemmAttnParams& a = p.a;
+  const int heads = a.heads, d = a.d;
+  const int BN = CROSS ? d : 3 * d;
+  const int NST = p.nst, stage_bytes = p.stage_bytes;
+  const int Cout = p.Cout;
+  const int nblk = (a.M + Z_TM - 1) / Z_TM;
+  const int nk_cta = (int)blockIdx.x < nblk ? (nblk - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int cph = d / KCH;
+  const int ochunks = heads * cph;
+  auto block_of_k = [&](int k) { const int b = (int)blockIdx.x + k * (int)gridDim.x; return a.rev ? nblk - 1 - b : b; };
+
+  if (tid == 0) {
+    for (int s = 0; s < Z_MAXST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], Z_EPI_WARPS / 2); }
+    mbar_init(&att_ready, Z_EPI_WARPS * 32);
+    mbar_init(&out_full, 1);
+    mbar_init(&out_empty, Z_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmW); }
+  if (warp == 1) tmem_alloc(&tmem_base_s, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;       // columns [0, Cout): OUT accumulator; [Cout + b * BN, ...): two projection accumulators
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx_j = (uint32_t)(Z_ABYTES + BN * 128), tx_o = (uint32_t)(Z_ABYTES + Cout * 128);
+      auto load_out = [&](int kk) {
+        mbar_wait(&att_ready, (uint32_t)kk & 1u);
+        z_fence_proxy_async();
+        const int j0 = kk * heads;
+        for (int oc = 0; oc < ochunks; ++oc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx_o);
+          const int hh = oc / cph, sub = oc - hh * cph;
+          const int slot = (j0 + hh) % p.nslot;
+          tma_load_3d(sa, &tmS, &full_bar[stage], sub * KCH, slot * Z_TM, (int)blockIdx.x);
+          tma_load_2d(sa + Z_ABYTES, &tmW, &full_bar[stage], oc * KCH, 0);
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
+        }
+      };
+      for (int k = 0; k < nk_cta; ++k) {
+        const int blk = block_of_k(k);
+        for (int h = 0; h < heads; ++h) {
+          if (h == Z_LA && k > 0) load_out(k - 1);
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sa = smem + stage * stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[stage], tx_j);
+            tma_load_3d(sa, &tmA, &full_bar[stage], kc * KCH, 0, blk * a.Sb);
+            tma_load_2d(sa + Z_ABYTES, &tmB, &full_bar[stage], kc * KCH, h * BN);
+            if (++stage == NST) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+      if (nk_cta > 0) load_out(nk_cta - 1);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    int stage = 0; uint32_t phase = 0;
+    int j = 0;
+    auto mma_out = [&](int kk) {
+      mbar_wait(&out_empty, ((uint32_t)kk & 1u) ^ 1u);
+      tc_fence_after();
+      for (int oc = 0; oc < ochunks; ++oc) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + Z_ABYTES);
+#pragma unroll
+          for (int kq = 0; kq < 4; ++kq)
+            umma<KIND>(tmem_base, adesc + (uint64_t)(2 * kq), bdesc + (uint64_t)(2 * kq), idesc_o, (uint32_t)((oc | kq) != 0));
+          umma_commit(&empty_bar[stage]);
+          if (oc == ochunks - 1) umma_commit(&out_full);
+        }
+        __syncwarp();
+        if (++stage == NST) { stage = 0; phase ^= 1u; }
+      }
+    };
+    for (int k = 0; k < nk_cta; ++k) {
+      for (int h = 0; h < heads; ++h, ++j) {
+        if (h == Z_LA && k > 0) mma_out(k - 1);
+        const int buf = j & 1;
+        mbar_wait(&acc_empty[buf], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(Cout + buf * BN);
+        for (int k0 = 0; k0 < a.kchunks; ++k0) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+            const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + Z_ABYTES);
+#pragma unroll
+            for (int kq = 0; kq < 4; ++kq)
+              umma<KIND>(tmem_d, adesc + (uint64_t)(2 * kq), bdesc + (uint64_t)(2 * kq), idesc, (uint32_t)((k0 | kq) != 0));
+            umma_commit(&empty_bar[stage]);
+            if (k0 == a.kchunks - 1) umma_commit(&acc_full[buf]);
+          }
+          __syncwarp();
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    if (nk_cta > 0) mma_out(nk_cta - 1);
+  } else {
+    // ------------------------------------------------------------------ attention warps (2..17): group gp owns accumulator gp
+    const int ew = warp - 2;
+    const int gp = ew >> 3;                 // head parity / projection accumulator of this warp
+    const int qd = warp & 3;                // TMEM lane quadrant
+    const int half = (ew >> 2) & 1;         // which 16 rows of the quadrant
+    const int r16 = qd * 32 + half * 16;    // first tile row of this warp's m16 tile
+    const int g = lane >> 2, q = lane & 3;
+    const int L = a.L;
+    const int bm = (!CROSS && L < 16) ? ~(L - 1) : 0;
+    float* vt = reinterpret_cast<float*>(smem + NST * stage_bytes) + (size_t)ew * 16 * Z_VLD;   // warp-private v tile (self only)
+    const size_t cta_slot0 = (size_t)blockIdx.x * p.nslot;
+    const uint32_t lane_addr = (uint32_t)r16 << 16;
+    const int sub = gp * 2 + half;          // this warp's column quarter of the OUT tile (four warps per quadrant)
+
+    auto final_epilogue = [&](int kk) {
+      const int m0 = block_of_k(kk) * Z_TM + qd * 32;      // first token row of this warp's quadrant
+      const int cols_w = Cout >> 2;
+      bool waited = false;
+      for (int cc = 0; cc < cols_w; cc += 32) {
+        const int col0 = sub * cols_w + cc;
+        // residual first (its HBM latency hides behind the accumulator wait): rows {g, g + 8} + 16 * hh, column pairs 8c + 2q
+        float2 r[2][2][4];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int mo = m0 + hh * 16 + rr * 8 + g;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              r[hh][rr][c] = (p.res && mo < a.M) ? *reinterpret_cast<const float2*>(p.res + (size_t)mo * p.ldres + col0 + 8 * c + 2 * q)
+                                                 : make_float2(0.f, 0.f);
+          }
+        if (!waited) { mbar_wait(&out_full, (uint32_t)kk & 1u); tc_fence_after(); waited = true; }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[16];
+          tmem_ld16x256_x4(tmem_base + ((uint32_t)(qd * 32 + hh * 16) << 16) + (uint32_t)col0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int no = col0 + 8 * c + 2 * q;
+            const float2 bv = p.bias_o ? __ldg(reinterpret_cast<const float2*>(p.bias_o + no)) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const int mo = m0 + hh * 16 + rr * 8 + g;
+              if (mo < a.M) {
+                const float ox = __uint_as_float(v[4 * c + 2 * rr]) + bv.x + r[hh][rr][c].x;
+                const float oy = __uint_as_float(v[4 * c + 2 * rr + 1]) + bv.y + r[hh][rr][c].y;
+                if (p.C32) *reinterpret_cast<float2*>(p.C32 + (size_t)mo * p.ldc + no) = make_float2(ox, oy);
+                if (p.Cop) SmemIO<KIND>::st2(p.Cop, (size_t)mo * p.ldcop + no, ox, oy);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&out_empty);
+    };
+
+    for (int k = 0; k < nk_cta; ++k) {
+      const int m0 = block_of_k(k) * Z_TM;
+      const int mrow = m0 + r16;
+      const int rows_valid = min(16, a.M - mrow);       // <= 0: this warp's rows are past the batch
+      for (int h = gp; h < heads; h += 2) {
+        const int j = k * heads + h;
+        const int buf = gp;
+        mbar_wait(&acc_full[buf], (uint32_t)(j >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t tq = tmem_base + lane_addr + (uint32_t)(Cout + buf * BN);
+        const size_t ob = ((cta_slot0 + (size_t)(j % p.nslot)) * Z_TM + (size_t)r16) * d;   // this warp's rows of the head's scratch slot
+        float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        float oc[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) { oc[n][0] = 0.f; oc[n][1] = 0.f; oc[n][2] = 0.f; oc[n][3] = 0.f; }
+        if constexpr (!CROSS) {
+          // ---- v: 16 key rows x 64 features -> warp-private tile (rows past the batch zeroed: they meet P = 0 in the packed tiles)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t vf[16];
+            tmem_ld16x256_x4(tq + (uint32_t)(2 * d + hf * 32), vf);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const bool z0 = g >= rows_valid, z1 = g + 8 >= rows_valid;
+              *reinterpret_cast<uint2*>(vt + g * Z_VLD + hf * 32 + 8 * c + 2 * q) =
+                  make_uint2(z0 ? 0u : to_tf32(__uint_as_float(vf[4 * c])), z0 ? 0u : to_tf32(__uint_as_float(vf[4 * c + 1])));
+              *reinterpret_cast<uint2*>(vt + (g + 8) * Z_VLD + hf * 32 + 8 * c + 2 * q) =
+                  make_uint2(z1 ? 0u : to_tf32(__uint_as_float(vf[4 * c + 2])), z1 ? 0u : to_tf32(__uint_as_float(vf[4 * c + 3])));
+            }
+          }
+          // ---- scores: q and k fragments straight from TMEM, 32 features per pass
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t qf[16], kf[16];
+            tmem_ld16x256_x4(tq + (uint32_t)(hf * 32), qf);
+            tmem_ld16x256_x4(tq + (uint32_t)(d + hf * 32), kf);
+            tmem_ld_wait();
+            add_q_bias<KIND>(qf, a.bias + h * d + hf * 32, q);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t af[4] = {qf[4 * c], qf[4 * c + 2], qf[4 * c + 1], qf[4 * c + 3]};
+              mma_tf32_16x8x8(sc[0], af, kf[4 * c], kf[4 * c + 1]);          // keys g
+              mma_tf32_16x8x8(sc[1], af, kf[4 * c + 2], kf[4 * c + 3]);      // keys g + 8
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);       // every TMEM read of this warp is complete
+          if (rows_valid > 0) {
+            uint32_t pa[2][4];
+            softmax_2tiles(sc, 16, a.scale, bm, g, q, pa);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const float* v0 = vt + (t * 8 + 2 * q) * Z_VLD + g;
+#pragma unroll
+              for (int n = 0; n < 8; ++n)
+                mma_tf32_16x8x8(oc[n], pa[t], __float_as_uint(v0[n * 8]), __float_as_uint(v0[Z_VLD + n * 8]));
+            }
+            store_o_tiles<KIND>(oc, p.scratch, ob, d, rows_valid, g, q);
+          }
+          __syncwarp();                                     // the v tile is rewritten by the next head
+        } else {
+          // ---- cross: q fragments from TMEM, K / V fragments from the fragment-ordered cache (permuted-k packing)
+          uint32_t qf[2][16];
+          tmem_ld16x256_x4(tq, qf[0]);
+          tmem_ld16x256_x4(tq + 32u, qf[1]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          if (rows_valid > 0) {
+            add_q_bias<KIND>(qf[0], a.bias + h * d, q);
+            add_q_bias<KIND>(qf[1], a.bias + h * d + 32, q);
+            const int G = 16 / L;                             // samples sharing this m16 tile
+            const int bs = mrow / L;
+            const int t0 = g / L, t1 = (g + 8) / L;           // sample of row g / row g + 8 inside the tile
+            float s0[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, s1[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+            for (int t = 0; t < G; ++t) {
+              const int b = (mrow + t * L < a.M) ? bs + t : bs;
+              const bool nul = a.kn && b >= a.n_cond;
+              const uint2* kf = reinterpret_cast<const uint2*>(nul ? a.kvf_n : a.kvf_c) + ((nul ? (size_t)0 : (size_t)b * heads) + h) * 1024;
+              float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                const int c = ks & 3;
+                const uint32_t af[4] = {qf[ks >> 2][4 * c], qf[ks >> 2][4 * c + 2], qf[ks >> 2][4 * c + 1], qf[ks >> 2][4 * c + 3]};
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                  const uint2 bb = __ldg(kf + (ks * 2 + nt) * 32 + lane);
+                  mma_tf32_16x8x8(st[nt], af, bb.x, bb.y);
+                }
+              }
+              if (t0 == t) { s0[0][0] = st[0][0]; s0[0][1] = st[0][1]; s0[1][0] = st[1][0]; s0[1][1] = st[1][1]; }
+              if (t1 == t) { s1[0][0] = st[0][2]; s1[0][1] = st[0][3]; s1[1][0] = st[1][2]; s1[1][1] = st[1][3]; }
+            }
+            sc[0][0] = s0[0][0]; sc[0][1] = s0[0][1]; sc[0][2] = s1[0][0]; sc[0][3] = s1[0][1];
+            sc[1][0] = s0[1][0]; sc[1][1] = s0[1][1]; sc[1][2] = s1[1][0]; sc[1][3] = s1[1][1];
+            uint32_t pa[2][4];
+            softmax_2tiles(sc, a.nk, a.scale, 0, g, q, pa);
+            for (int t = 0; t < G; ++t) {
+              const int b = (mrow + t * L < a.M) ? bs + t : bs;
+              const bool nul = a.kn && b >= a.n_cond;
+              const uint2* vf = reinterpret_cast<const uint2*>(nul ? a.kvf_n : a.kvf_c) + ((nul ? (size_t)0 : (size_t)b * heads) + h) * 1024 + 512;
+              const bool own0 = t0 == t, own1 = t1 == t;
+#pragma unroll
+              for (int kt = 0; kt < 2; ++kt) {
+                const uint32_t af[4] = {own0 ? pa[kt][0] : 0u, own1 ? pa[kt][1] : 0u, own0 ? pa[kt][2] : 0u, own1 ? pa[kt][3] : 0u};
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                  const uint2 bb = __ldg(vf + (kt * 8 + n) * 32 + lane);
+                  mma_tf32_16x8x8(oc[n], af, bb.x, bb.y);
+                }
+              }
+            }
+            store_o_tiles<KIND>(oc, p.scratch, ob, d, rows_valid, g, q);
+          }
+        }
+        if (h + 2 >= heads) {
+          // this thread's last head of the block: publish its head outputs to the async proxy, then tell the producer
+          z_fence_proxy_async();
+          mbar_arrive(&att_ready);
+        }
+        if (h < 2 && k > 0) final_epilogue(k - 1);            // after this warp's first head of the next block (Z_LA = 2)
+      }
+    }
+    if (nk_cta > 0) final_epilogue(nk_cta - 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace tc
+
+static const size_t Z_SMEM_LIMIT = 232448 - 1024;
+
+static bool attn_frag_config(int d, int cross, int Cout, int* nst, int* stage_bytes, unsigned* tmem_cols, size_t* smem) {
+  const int BN = cross ? d : 3 * d;
+  const size_t sj = tc::Z_ABYTES + (((size_t)BN * 128 + 1023) & ~(size_t)1023), so = tc::Z_ABYTES + (size_t)Cout * 128;
+  const size_t stage = sj > so ? sj : so;
+  const size_t stg = cross ? 0 : (size_t)tc::Z_EPI_WARPS * 16 * tc::Z_VLD * 4;
+  int n = (int)((Z_SMEM_LIMIT - stg - 1024) / stage);
+  if (n > tc::Z_MAXST) n = tc::Z_MAXST;
+  if (n < 2) return false;
+  if (Cout + 2 * BN > 512) return false;                  // two projection accumulators (one per warp group) + OUT
+  unsigned cols = 32;
+  while ((int)cols < Cout + 2 * BN) cols <<= 1;
+  *nst = n; *stage_bytes = (int)stage; *tmem_cols = cols; *smem = (size_t)n * stage + stg + 1024;
+  return true;
+}
+
+bool attn_frag_supported(int kind, int C, int L, int heads, int d, int cross, int Cout) {
+  const int kch = kind == 1 ? 32 : 64;
+  if (kind != 1 && kind != 2) return false;
+  if (d != 64 || heads < 2 || (heads & 1) || C % kch) return false;
+  if (!(L == 4 || L == 8 || L == 16)) return false;
+  if (Cout < 128 || Cout > 256 || Cout % 128) return false;   // four column quarters of >= 32 columns
+  int nst, sb; unsigned tc_; size_t sm;
+  return attn_frag_config(d, cross, Cout, &nst, &sb, &tc_, &sm);
+}
+
+typedef void (*AttnFragKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnLayerParams,
+                               const uint32_t, const uint32_t);
+static AttnFragKernel attn_frag_variant(int kind, int cross) {
+  static const AttnFragKernel tab[2][2] = {{tc::attn_frag_kernel<1, 0>, tc::attn_frag_kernel<1, 3>},
+                                           {tc::attn_frag_kernel<2, 0>, tc::attn_frag_kernel<2, 3>}};
+  return tab[kind == 1 ? 0 : 1][cross ? 1 : 0];
+}
+
+cudaError_t init_attn_frag() {
+  for (int kind = 1; kind <= 2; ++kind)
+    for (int cross = 0; cross < 2; ++cross) {
+      cudaError_t e = cudaFuncSetAttribute(attn_frag_variant(kind, cross), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Z_SMEM_LIMIT);
+      if (e != cudaSuccess) return e;
+    }
+  return cudaSuccess;
+}
+
+cudaError_t launch_attn_frag(const void* tmA, const void* tmB, const void* tmS, const void* tmW, const AttnLayerParams& pin, int kind,
+                             cudaStream_t s) {
+  AttnLayerParams p = pin;
+  const GemmAttnParams& a = p.a;
+  if (a.M <= 0) return cudaSuccess;
+  size_t smem = 0;
+  if (!attn_frag_config(a.d, a.cross, p.Cout, &p.nst, &p.stage_bytes, &p.tmem_cols, &smem)) return cudaErrorInvalidValue;
+  if (a.cross && !a.kvf_c) return cudaErrorInvalidValue;
+  p.nacc = 2;
+  p.nslot = a.heads + tc::Z_LA;
+  const int BN = a.cross ? a.d : 3 * a.d;
+  const uint32_t fmt = kind == 1 ? 2u : 1u;
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(tc::Z_TM >> 4) << 24);
+  const uint32_t idesc_o = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(tc::Z_TM >> 4) << 24);
+  const int nblk = (a.M + tc::Z_TM - 1) / tc::Z_TM;
+  const int sms = attn_layer_sms();
+  const unsigned grid = (unsigned)(nblk < sms ? nblk : sms);
+  attn_frag_variant(kind, a.cross)<<<grid, tc::Z_THREADS, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(tmA),
+                                                                     *reinterpret_cast<const CUtensorMap*>(tmB),
+                                                                     *reinterpret_cast<const CUtensorMap*>(tmS),
+                                                                     *reinterpret_cast<const CUtensorMap*>(tmW), p, idesc, idesc_o);
+  return cudaGetLastError();
+}
+
+}  // namespace mdt

@@ -921,7 +921,7 @@ cudaError_t launch_inpaint(int mode, float* x, float* xin, const float* source, 
 //                               V: f = ktile * 8 + ntile   b0 = V[8 ktile + 2q][8 ntile + g], b1 = V[8 ktile + 2q + 1][8 ntile + g]
 // (g = lane / 4, q = lane % 4; the V key permutation matches the P -> A-fragment reuse in attn_math.cuh).  Keys >= nk read as 0.
 // Values are rounded to tf32.  One 256-byte coalesced load per fragment replaces the cp.async staging + shared-memory fragment loads.
-__global__ void kv_fragment_pack_kernel(const float* __restrict__ kv, uint2* __restrict__ out, long long B, int nk, int heads, int d) {
+__global__ void kv_fragment_pack_kernel(const float* __restrict__ kv, uint2* __restrict__ out, long long B, int nk, int heads, int d, int kperm) {
   const long long bh = blockIdx.x;
   const long long b = bh / heads;
   const int h = (int)(bh - b * heads);
@@ -932,8 +932,10 @@ __global__ void kv_fragment_pack_kernel(const float* __restrict__ kv, uint2* __r
     const int which = idx >> 9, f = (idx >> 5) & 15, lane = idx & 31, g = lane >> 2, q = lane & 3;
     float b0 = 0.f, b1 = 0.f;
     if (which == 0) {
-      const int key = (f & 1) * 8 + g, c0 = (f >> 1) * 8 + q;
-      if (key < nk) { b0 = base[(size_t)key * ldkv + c0]; b1 = base[(size_t)key * ldkv + c0 + 4]; }
+      // kperm: the q fragments come from tcgen05.ld.16x256b (thread (g, q) holds columns 2q, 2q + 1 of every 8-column group), so the
+      // k index is relabelled k = q <-> column 2q, k = q + 4 <-> column 2q + 1 on both operands (gemm_attn_frag.cu)
+      const int key = (f & 1) * 8 + g, c0 = (f >> 1) * 8 + (kperm ? 2 * q : q), c1 = c0 + (kperm ? 1 : 4);
+      if (key < nk) { b0 = base[(size_t)key * ldkv + c0]; b1 = base[(size_t)key * ldkv + c1]; }
     } else {
       const int j0 = (f >> 3) * 8 + 2 * q, col = (f & 7) * 8 + g;
       const float* v = base + heads * d;
@@ -947,10 +949,10 @@ __global__ void kv_fragment_pack_kernel(const float* __restrict__ kv, uint2* __r
   }
 }
 
-cudaError_t launch_kv_fragment_pack(const float* kv, void* out, long long B, int nk, int heads, int d, cudaStream_t s) {
+cudaError_t launch_kv_fragment_pack(const float* kv, void* out, long long B, int nk, int heads, int d, int kperm, cudaStream_t s) {
   if (B <= 0) return cudaSuccess;
   if (d != 64 || nk > 16 || nk < 1) return cudaErrorInvalidValue;
-  kv_fragment_pack_kernel<<<(unsigned)(B * heads), 256, 0, s>>>(kv, reinterpret_cast<uint2*>(out), B, nk, heads, d);
+  kv_fragment_pack_kernel<<<(unsigned)(B * heads), 256, 0, s>>>(kv, reinterpret_cast<uint2*>(out), B, nk, heads, d, kperm);
   return cudaGetLastError();
 }
 

@@ -154,7 +154,8 @@ cudaError_t launch_inpaint(int mode, float* x, float* xin, const float* source, 
                            float sigma, float c_in, unsigned long long seed, unsigned long long sample_offset, int stream, int B,
                            int P, int L, int cfg, float* out, cudaStream_t s);
 cudaError_t launch_set_run_params(RunParams* dst, const RunParams& v, cudaStream_t s);
-cudaError_t launch_kv_fragment_pack(const float* kv, void* out, long long B, int nk, int heads, int d, cudaStream_t s);
+// kperm != 0: K fragments in the permuted k order of gemm_attn_frag.cu (b0 = K[key][8 ks + 2q], b1 = K[key][8 ks + 2q + 1])
+cudaError_t launch_kv_fragment_pack(const float* kv, void* out, long long B, int nk, int heads, int d, int kperm, cudaStream_t s);
 cudaError_t launch_decode_tokens(const uint8_t* tokens, const uint8_t* lut, uint8_t* out, int* lengths, long long B, int L, cudaStream_t s);
 cudaError_t launch_set_int(int* dst, int v, cudaStream_t s);
 cudaError_t launch_add_int(int* dst, int v, cudaStream_t s);
@@ -250,6 +251,12 @@ cudaError_t init_attn_layer();
 // tmW: out-projection weight [Cout][heads * d] with a (KCH x Cout) box
 cudaError_t launch_attn_layer(const void* tmA, const void* tmB, const void* tmS, const void* tmW, const AttnLayerParams& p, int kind,
                               cudaStream_t s);
+
+// same contract with the q / k fragments read straight from TMEM and sixteen attention warps (gemm_attn_frag.cu)
+bool attn_frag_supported(int kind, int C, int L, int heads, int d, int cross, int Cout);
+cudaError_t init_attn_frag();
+cudaError_t launch_attn_frag(const void* tmA, const void* tmB, const void* tmS, const void* tmW, const AttnLayerParams& p, int kind,
+                             cudaStream_t s);
 
 // ---- FeedForward chain (gemm_chain.cu): Linear -> GELU -> Linear + residual (+ LayerNorm of the result) in one kernel ---------
 struct FFChainParams {

@@ -78,6 +78,7 @@ struct Op {
   alignas(64) unsigned char tmD[128];
   bool cross = false;  // attention reads the precomputed conditioning K/V
   bool umma_core = false;  // fused attention with the softmax-attention core on tcgen05 (gemm_attn_umma.cu)
+  bool frag = false;       // attention layer with q / k fragments straight from TMEM (gemm_attn_frag.cu)
   int cross_layer = -1;
   // upsample gather / permute
   const float* in0 = nullptr; const float* in1 = nullptr; const float* in2 = nullptr; float* out = nullptr;
@@ -107,6 +108,7 @@ struct CrossLayer {
   void* kv_null_op = nullptr;
   void* kvf_cond = nullptr;            // fragment-ordered tf32 copies for the packed cross-attention path (L <= 8), 8 KB per (sample, head)
   void* kvf_null = nullptr;
+  int kperm = 0;                       // K fragments packed in the permuted k order of gemm_attn_frag.cu
 };
 
 struct mdt_plan {
@@ -394,6 +396,11 @@ struct Builder {
     if (cross && !packed_cross) return false;
     return attn_layer_supported(pl.prec, C, L, pl.cfg.heads, pl.cfg.head_features, cross, C);
   }
+  bool frag_ok(int C, int L, int cross) const {
+    const char* e = getenv("MDT_ATTN_FRAG");
+    if (e && e[0] == '0') return false;
+    return attn_frag_supported(pl.prec, C, L, pl.cfg.heads, pl.cfg.head_features, cross, C);
+  }
   void emit_attn_layer(std::vector<Op>& prog, const void* A, int C, int L, const float* dW32, const float* bias_q, int cross,
                        int cross_layer, const void* kn_flag, const void* kvf_c, const void* kvf_n, const float* dWo32,
                        const float* bias_o, float* t, void* cop) {
@@ -421,6 +428,8 @@ struct Builder {
     if (make_tmap_weight(op.tmB, wop, pl.prec, (long long)C, heads * BN, BN) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(layer weight) failed");
     if (make_tmap_act(op.tmC, pl.attn_scratch, pl.prec, d, attn_layer_slots(heads) * 128, (long long)attn_layer_sms()) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(layer scratch) failed");
     if (make_tmap_weight(op.tmD, woo, pl.prec, (long long)Hd, C, C) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(layer out-projection) failed");
+    op.frag = frag_ok(C, L, cross);
+    if (cross && cross_layer >= 0) pl.cross[cross_layer].kperm = op.frag ? 1 : 0;
     emit(prog, op);
   }
 
@@ -1017,7 +1026,7 @@ static std::string describe(const Op& op, int Beff) {
     case OP_GEMM_TMA: snprintf(b, sizeof b, "gemm_tma  M=%d N=%d K=%dx%d L=%d bn=%d%s%s%s%s", Beff * op.rps, op.tg.N, op.tg.taps, op.tg.C, op.tg.L, op.tg.BN,
                                op.tg.gn_L ? " +gn" : "", op.tg.res ? " +res" : "", op.tg.act ? " +act" : "", h); break;
     case OP_GEMM_ATTN: snprintf(b, sizeof b, "gemm_attn%s %s M=%d C=%d L=%d%s", op.umma_core ? "_umma" : "", op.cross ? "cross" : "self", Beff * op.rps, op.gat.C, op.gat.L, h); break;
-    case OP_ATTN_LAYER: snprintf(b, sizeof b, "attn_layer %s M=%d C=%d L=%d%s%s", op.cross ? "cross" : "self", Beff * op.rps, op.al.a.C, op.al.a.L, op.al.Cop ? " +cop" : "", h); break;
+    case OP_ATTN_LAYER: snprintf(b, sizeof b, "attn_%s %s M=%d C=%d L=%d%s%s", op.frag ? "frag " : "layer", op.cross ? "cross" : "self", Beff * op.rps, op.al.a.C, op.al.a.L, op.al.Cop ? " +cop" : "", h); break;
     case OP_GEMM: snprintf(b, sizeof b, "gemm      M=%d N=%d K=%d taps=%d stride=%d%s", Beff * op.rps, op.g.N, op.g.K, op.g.a.taps, op.g.a.stride, h); break;
     case OP_GN_APPLY: snprintf(b, sizeof b, "gn_apply  B=%d L=%d C=%d%s%s", Beff, op.ga.L, op.ga.c0 + op.ga.c1, op.ga.raw ? " +raw" : "", h); break;
     case OP_LN_APPLY: snprintf(b, sizeof b, "ln_apply  rows=%d C=%d%s", Beff * op.rps, op.la.C, h); break;
@@ -1084,7 +1093,8 @@ static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_con
       case OP_ATTN_LAYER: {
         AttnLayerParams y = op.al; y.a.M = Beff * op.rps; y.a.rev = rev;
         if (op.cross) { y.a.nk = n_ctx; y.a.kv_sample_stride = (long long)n_ctx * y.a.ldkv; y.a.n_cond = n_cond; }
-        CK(launch_attn_layer(op.tmA, op.tmB, op.tmC, op.tmD, y, pl.prec, s));
+        CK(op.frag ? launch_attn_frag(op.tmA, op.tmB, op.tmC, op.tmD, y, pl.prec, s)
+                   : launch_attn_layer(op.tmA, op.tmB, op.tmC, op.tmD, y, pl.prec, s));
         pl.launches++; break;
       }
       case OP_GEMM_FF: {
@@ -1161,13 +1171,13 @@ static void run_context(mdt_plan& pl, const float* cond_dev, int Bc, int n_ctx, 
     g.a.stats = pl.emb_stats; g.a.stats_mode = 1;
     CK(launch_gemm_fp32(g, s)); pl.launches++;
     if (cl.kv_cond_op) { CK(convert_weights_tc(cl.kv_cond, cl.kv_cond_op, (long long)Bc * n_ctx * 2 * Hd, pl.prec, s)); pl.launches++; }
-    if (cl.kvf_cond) { CK(launch_kv_fragment_pack(cl.kv_cond, cl.kvf_cond, Bc, n_ctx, c.heads, c.head_features, s)); pl.launches++; }
+    if (cl.kvf_cond) { CK(launch_kv_fragment_pack(cl.kv_cond, cl.kvf_cond, Bc, n_ctx, c.heads, c.head_features, cl.kperm, s)); pl.launches++; }
     if (cfg) {
       GemmParams gn = dense(pl.w_null_emb, F, cl.wkv, cl.bkv, 2 * Hd, n_ctx, 0, cl.kv_null, false);
       gn.a.stats = pl.emb_null_stats; gn.a.stats_mode = 1;
       CK(launch_gemm_fp32(gn, s)); pl.launches++;
       if (cl.kv_null_op) { CK(convert_weights_tc(cl.kv_null, cl.kv_null_op, (long long)n_ctx * 2 * Hd, pl.prec, s)); pl.launches++; }
-      if (cl.kvf_null) { CK(launch_kv_fragment_pack(cl.kv_null, cl.kvf_null, 1, n_ctx, c.heads, c.head_features, s)); pl.launches++; }
+      if (cl.kvf_null) { CK(launch_kv_fragment_pack(cl.kv_null, cl.kvf_null, 1, n_ctx, c.heads, c.head_features, cl.kperm, s)); pl.launches++; }
     }
   }
 }
@@ -1279,6 +1289,7 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
     CK(init_gemm_attn());
     CK(init_gemm_attn_umma());
     CK(init_attn_layer());
+    CK(init_attn_frag());
     CK(init_ff_chain());
     pl->cfg = *cfg; pl->device = device; pl->prec = cfg->precision;
     pl->P = cfg->in_channels; pl->L0 = cfg->length; pl->Hd = cfg->heads * cfg->head_features; pl->F = cfg->ctx_features;
