@@ -98,7 +98,8 @@ __device__ __forceinline__ void store_o_tiles(const float (&oc)[8][4], void* out
   }
 }
 
-// MODE: 0 self (L in {4, 8, 16}: 16 rows = 16 / L samples, block-diagonal mask when L < 16);  3 cross on the fragment-ordered cache
+// MODE: 0 self (L in {4, 8, 16}: 16 rows = 16 / L samples, block-diagonal mask when L < 16);  4 / 8 / 16: cross-attention on the
+// fragment-ordered cache with that many query rows per sample (compile time: 16 / MODE samples share the m16 tile)
 template <int KIND, int MODE>
 __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
@@ -107,7 +108,9 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
                                                                 const AttnLayerParams p, const uint32_t idesc,
                                                                 const uint32_t idesc_o) {
   constexpr int KCH = (KIND == 1) ? 32 : 64;
-  constexpr bool CROSS = MODE >= 2;
+  constexpr bool CROSS = MODE != 0;
+  constexpr int LQ = CROSS ? MODE : 16;
+  constexpr int G = 16 / LQ;                // samples sharing one m16 tile (cross)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[Z_MAXST];
   __shared__ __align__(8) uint64_t empty_bar[Z_MAXST];
@@ -125,10 +128,17 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
   const int NST = p.nst, stage_bytes = p.stage_bytes;
   const int Cout = p.Cout;
   const int nblk = (a.M + Z_TM - 1) / Z_TM;
-  const int nk_cta = (int)blockIdx.x < nblk ? (nblk - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int cph = d / KCH;
   const int ochunks = heads * cph;
-  auto block_of_k = [&](int k) { const int b = (int)blockIdx.x + k * (int)gridDim.x; return a.rev ? nblk - 1 - b : b; };
+  // fused: a work item is a whole row block (its heads in sequence, then the out-projection); otherwise one (row block, head) pair
+  // whose head output goes to the global attention tensor (the out-projection is a separate GEMM) -- eight times more items, which is
+  // what balances short levels (256 row blocks on 148 SMs) across the grid
+  const bool fused = p.fused != 0;
+  const int nitems = fused ? nblk : nblk * heads;
+  const int nk_cta = (int)blockIdx.x < nitems ? (nitems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int njobs = fused ? nk_cta * heads : nk_cta;
+  auto item_of_k = [&](int k) { const int b = (int)blockIdx.x + k * (int)gridDim.x; return a.rev ? nitems - 1 - b : b; };
+  auto block_of_k = [&](int k) { return item_of_k(k); };      // fused mode: item == row block
 
   if (tid == 0) {
     for (int s = 0; s < Z_MAXST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -138,7 +148,10 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
     mbar_init(&out_empty, Z_EPI_WARPS);
     fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmW); }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+    if (p.fused) { tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmW); }     // the unfused variant carries no scratch / out-projection maps
+  }
   if (warp == 1) tmem_alloc(&tmem_base_s, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -165,21 +178,22 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
           if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
       };
-      for (int k = 0; k < nk_cta; ++k) {
-        const int blk = block_of_k(k);
-        for (int h = 0; h < heads; ++h) {
-          if (h == Z_LA && k > 0) load_out(k - 1);
-          for (int kc = 0; kc < a.kchunks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            uint8_t* sa = smem + stage * stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[stage], tx_j);
-            tma_load_3d(sa, &tmA, &full_bar[stage], kc * KCH, 0, blk * a.Sb);
-            tma_load_2d(sa + Z_ABYTES, &tmB, &full_bar[stage], kc * KCH, h * BN);
-            if (++stage == NST) { stage = 0; phase ^= 1u; }
-          }
+      int k = 0, h = 0;
+      for (int j = 0; j < njobs; ++j) {
+        int blk;
+        if (fused) { blk = block_of_k(k); if (h == Z_LA && k > 0) load_out(k - 1); }
+        else { const int it = item_of_k(j); blk = it / heads; h = it - blk * heads; }
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx_j);
+          tma_load_3d(sa, &tmA, &full_bar[stage], kc * KCH, 0, blk * a.Sb);
+          tma_load_2d(sa + Z_ABYTES, &tmB, &full_bar[stage], kc * KCH, h * BN);
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
+        if (fused && ++h == heads) { h = 0; ++k; }
       }
-      if (nk_cta > 0) load_out(nk_cta - 1);
+      if (fused && nk_cta > 0) load_out(nk_cta - 1);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -204,9 +218,10 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
         if (++stage == NST) { stage = 0; phase ^= 1u; }
       }
     };
-    for (int k = 0; k < nk_cta; ++k) {
-      for (int h = 0; h < heads; ++h, ++j) {
-        if (h == Z_LA && k > 0) mma_out(k - 1);
+    int k = 0, h = 0;
+    for (; j < njobs; ++j) {
+      {
+        if (fused && h == Z_LA && k > 0) mma_out(k - 1);
         const int buf = j & 1;
         mbar_wait(&acc_empty[buf], ((uint32_t)(j >> 1) & 1u) ^ 1u);
         tc_fence_after();
@@ -226,9 +241,10 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
           __syncwarp();
           if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
+        if (fused && ++h == heads) { h = 0; ++k; }
       }
     }
-    if (nk_cta > 0) mma_out(nk_cta - 1);
+    if (fused && nk_cta > 0) mma_out(nk_cta - 1);
   } else {
     // ------------------------------------------------------------------ attention warps (2..17): group gp owns accumulator gp
     const int ew = warp - 2;
@@ -290,17 +306,38 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
       if (lane == 0) mbar_arrive(&out_empty);
     };
 
-    for (int k = 0; k < nk_cta; ++k) {
-      const int m0 = block_of_k(k) * Z_TM;
+    for (int j = gp; j < njobs; j += 2) {
+      int k, h, m0;
+      if (fused) { k = j / heads; h = j - k * heads; m0 = block_of_k(k) * Z_TM; }
+      else { const int it = item_of_k(j); k = it / heads; h = it - k * heads; m0 = k * Z_TM; }
       const int mrow = m0 + r16;
       const int rows_valid = min(16, a.M - mrow);       // <= 0: this warp's rows are past the batch
-      for (int h = gp; h < heads; h += 2) {
-        const int j = k * heads + h;
+      {
         const int buf = gp;
+        // cross: the K / V fragment blocks of this tile's samples and head; with one sample per tile the K fragments are fetched
+        // before the accumulator wait (they do not depend on the projection), so their L2 / HBM latency hides behind it
+        const uint2* kvp[G];
+        uint2 kb[16];
+        if constexpr (CROSS) {
+          const int bs = mrow / LQ;
+#pragma unroll
+          for (int t = 0; t < G; ++t) {
+            const int b = (mrow + t * LQ < a.M) ? bs + t : bs;            // samples past the batch: any valid block, rows not stored
+            const bool nul = a.kn && b >= a.n_cond;
+            kvp[t] = reinterpret_cast<const uint2*>(nul ? a.kvf_n : a.kvf_c) + ((nul ? (size_t)0 : (size_t)b * heads) + h) * 1024;
+          }
+          if (G == 1 && rows_valid > 0) {
+#pragma unroll
+            for (int f = 0; f < 16; ++f) kb[f] = __ldg(kvp[0] + f * 32 + lane);
+          }
+        }
         mbar_wait(&acc_full[buf], (uint32_t)(j >> 1) & 1u);
         tc_fence_after();
         const uint32_t tq = tmem_base + lane_addr + (uint32_t)(Cout + buf * BN);
-        const size_t ob = ((cta_slot0 + (size_t)(j % p.nslot)) * Z_TM + (size_t)r16) * d;   // this warp's rows of the head's scratch slot
+        // fused: this warp's rows of the head's scratch slot; otherwise its rows / head columns of the global attention tensor
+        void* const obuf = fused ? p.scratch : a.att;
+        const int ldo = fused ? d : a.ldo;
+        const size_t ob = fused ? ((cta_slot0 + (size_t)(j % p.nslot)) * Z_TM + (size_t)r16) * d : (size_t)mrow * a.ldo + (size_t)h * d;
         float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         float oc[8][4];
 #pragma unroll
@@ -349,7 +386,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
               for (int n = 0; n < 8; ++n)
                 mma_tf32_16x8x8(oc[n], pa[t], __float_as_uint(v0[n * 8]), __float_as_uint(v0[Z_VLD + n * 8]));
             }
-            store_o_tiles<KIND>(oc, p.scratch, ob, d, rows_valid, g, q);
+            store_o_tiles<KIND>(oc, obuf, ob, ldo, rows_valid, g, q);
           }
           __syncwarp();                                     // the v tile is rewritten by the next head
         } else {
@@ -364,59 +401,68 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
           if (rows_valid > 0) {
             add_q_bias<KIND>(qf[0], a.bias + h * d, q);
             add_q_bias<KIND>(qf[1], a.bias + h * d + 32, q);
-            const int G = 16 / L;                             // samples sharing this m16 tile
-            const int bs = mrow / L;
-            const int t0 = g / L, t1 = (g + 8) / L;           // sample of row g / row g + 8 inside the tile
-            float s0[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, s1[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-            for (int t = 0; t < G; ++t) {
-              const int b = (mrow + t * L < a.M) ? bs + t : bs;
-              const bool nul = a.kn && b >= a.n_cond;
-              const uint2* kf = reinterpret_cast<const uint2*>(nul ? a.kvf_n : a.kvf_c) + ((nul ? (size_t)0 : (size_t)b * heads) + h) * 1024;
-              float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+            float st[G][2][4];
 #pragma unroll
-              for (int ks = 0; ks < 8; ++ks) {
-                const int c = ks & 3;
-                const uint32_t af[4] = {qf[ks >> 2][4 * c], qf[ks >> 2][4 * c + 2], qf[ks >> 2][4 * c + 1], qf[ks >> 2][4 * c + 3]};
+            for (int t = 0; t < G; ++t)
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) { st[t][nt][0] = 0.f; st[t][nt][1] = 0.f; st[t][nt][2] = 0.f; st[t][nt][3] = 0.f; }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const int c = ks & 3;
+              const uint32_t af[4] = {qf[ks >> 2][4 * c], qf[ks >> 2][4 * c + 2], qf[ks >> 2][4 * c + 1], qf[ks >> 2][4 * c + 3]};
+#pragma unroll
+              for (int t = 0; t < G; ++t)
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
-                  const uint2 bb = __ldg(kf + (ks * 2 + nt) * 32 + lane);
-                  mma_tf32_16x8x8(st[nt], af, bb.x, bb.y);
+                  const uint2 bb = (G == 1) ? kb[ks * 2 + nt] : __ldg(kvp[t] + (ks * 2 + nt) * 32 + lane);
+                  mma_tf32_16x8x8(st[t][nt], af, bb.x, bb.y);
                 }
-              }
-              if (t0 == t) { s0[0][0] = st[0][0]; s0[0][1] = st[0][1]; s0[1][0] = st[1][0]; s0[1][1] = st[1][1]; }
-              if (t1 == t) { s1[0][0] = st[0][2]; s1[0][1] = st[0][3]; s1[1][0] = st[1][2]; s1[1][1] = st[1][3]; }
             }
-            sc[0][0] = s0[0][0]; sc[0][1] = s0[0][1]; sc[0][2] = s1[0][0]; sc[0][3] = s1[0][1];
-            sc[1][0] = s0[1][0]; sc[1][1] = s0[1][1]; sc[1][2] = s1[1][0]; sc[1][3] = s1[1][1];
+            // one sample per tile: fetch the V fragments now, their latency hides behind the softmax
+            uint2 vb[16];
+            if (G == 1) {
+#pragma unroll
+              for (int f = 0; f < 16; ++f) vb[f] = __ldg(kvp[0] + 512 + f * 32 + lane);
+            }
+            // row g belongs to sample t0 = g / LQ, row g + 8 to sample t1 = (g + 8) / LQ: pick their score blocks
+            const int t0 = g / LQ, t1 = (g + 8) / LQ;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+              float a0 = st[0][nt][0], a1 = st[0][nt][1], b0 = st[0][nt][2], b1 = st[0][nt][3];
+#pragma unroll
+              for (int t = 1; t < G; ++t) {
+                if (t0 == t) { a0 = st[t][nt][0]; a1 = st[t][nt][1]; }
+                if (t1 == t) { b0 = st[t][nt][2]; b1 = st[t][nt][3]; }
+              }
+              sc[nt][0] = a0; sc[nt][1] = a1; sc[nt][2] = b0; sc[nt][3] = b1;
+            }
             uint32_t pa[2][4];
             softmax_2tiles(sc, a.nk, a.scale, 0, g, q, pa);
+#pragma unroll
             for (int t = 0; t < G; ++t) {
-              const int b = (mrow + t * L < a.M) ? bs + t : bs;
-              const bool nul = a.kn && b >= a.n_cond;
-              const uint2* vf = reinterpret_cast<const uint2*>(nul ? a.kvf_n : a.kvf_c) + ((nul ? (size_t)0 : (size_t)b * heads) + h) * 1024 + 512;
               const bool own0 = t0 == t, own1 = t1 == t;
 #pragma unroll
               for (int kt = 0; kt < 2; ++kt) {
                 const uint32_t af[4] = {own0 ? pa[kt][0] : 0u, own1 ? pa[kt][1] : 0u, own0 ? pa[kt][2] : 0u, own1 ? pa[kt][3] : 0u};
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
-                  const uint2 bb = __ldg(vf + (kt * 8 + n) * 32 + lane);
+                  const uint2 bb = (G == 1) ? vb[kt * 8 + n] : __ldg(kvp[t] + 512 + (kt * 8 + n) * 32 + lane);
                   mma_tf32_16x8x8(oc[n], af, bb.x, bb.y);
                 }
               }
             }
-            store_o_tiles<KIND>(oc, p.scratch, ob, d, rows_valid, g, q);
+            store_o_tiles<KIND>(oc, obuf, ob, ldo, rows_valid, g, q);
           }
         }
-        if (h + 2 >= heads) {
+        if (fused && h + 2 >= heads) {
           // this thread's last head of the block: publish its head outputs to the async proxy, then tell the producer
           z_fence_proxy_async();
           mbar_arrive(&att_ready);
         }
-        if (h < 2 && k > 0) final_epilogue(k - 1);            // after this warp's first head of the next block (Z_LA = 2)
+        if (fused && h < 2 && k > 0) final_epilogue(k - 1);   // after this warp's first head of the next block (Z_LA = 2)
       }
     }
-    if (nk_cta > 0) final_epilogue(nk_cta - 1);
+    if (fused && nk_cta > 0) final_epilogue(nk_cta - 1);
   }
   tc_fence_before();
   __syncthreads();
@@ -427,9 +473,10 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
 
 static const size_t Z_SMEM_LIMIT = 232448 - 1024;
 
+// Cout = 0: unfused (no out-projection accumulator, no out-projection stages)
 static bool attn_frag_config(int d, int cross, int Cout, int* nst, int* stage_bytes, unsigned* tmem_cols, size_t* smem) {
   const int BN = cross ? d : 3 * d;
-  const size_t sj = tc::Z_ABYTES + (((size_t)BN * 128 + 1023) & ~(size_t)1023), so = tc::Z_ABYTES + (size_t)Cout * 128;
+  const size_t sj = tc::Z_ABYTES + (((size_t)BN * 128 + 1023) & ~(size_t)1023), so = Cout ? tc::Z_ABYTES + (size_t)Cout * 128 : 0;
   const size_t stage = sj > so ? sj : so;
   const size_t stg = cross ? 0 : (size_t)tc::Z_EPI_WARPS * 16 * tc::Z_VLD * 4;
   int n = (int)((Z_SMEM_LIMIT - stg - 1024) / stage);
@@ -442,28 +489,31 @@ static bool attn_frag_config(int d, int cross, int Cout, int* nst, int* stage_by
   return true;
 }
 
+// Cout = 0 asks for the unfused variant (head outputs to the global attention tensor, out-projection elsewhere)
 bool attn_frag_supported(int kind, int C, int L, int heads, int d, int cross, int Cout) {
   const int kch = kind == 1 ? 32 : 64;
   if (kind != 1 && kind != 2) return false;
   if (d != 64 || heads < 2 || (heads & 1) || C % kch) return false;
   if (!(L == 4 || L == 8 || L == 16)) return false;
-  if (Cout < 128 || Cout > 256 || Cout % 128) return false;   // four column quarters of >= 32 columns
+  if (Cout != 0 && (Cout < 128 || Cout > 256 || Cout % 128)) return false;   // four column quarters of >= 32 columns
   int nst, sb; unsigned tc_; size_t sm;
   return attn_frag_config(d, cross, Cout, &nst, &sb, &tc_, &sm);
 }
 
 typedef void (*AttnFragKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnLayerParams,
                                const uint32_t, const uint32_t);
-static AttnFragKernel attn_frag_variant(int kind, int cross) {
-  static const AttnFragKernel tab[2][2] = {{tc::attn_frag_kernel<1, 0>, tc::attn_frag_kernel<1, 3>},
-                                           {tc::attn_frag_kernel<2, 0>, tc::attn_frag_kernel<2, 3>}};
-  return tab[kind == 1 ? 0 : 1][cross ? 1 : 0];
+// mode: 0 self; 4 / 8 / 16 cross with that many query rows per sample
+static AttnFragKernel attn_frag_variant(int kind, int mode) {
+  static const AttnFragKernel tab[2][4] = {
+      {tc::attn_frag_kernel<1, 0>, tc::attn_frag_kernel<1, 4>, tc::attn_frag_kernel<1, 8>, tc::attn_frag_kernel<1, 16>},
+      {tc::attn_frag_kernel<2, 0>, tc::attn_frag_kernel<2, 4>, tc::attn_frag_kernel<2, 8>, tc::attn_frag_kernel<2, 16>}};
+  return tab[kind == 1 ? 0 : 1][mode == 0 ? 0 : (mode == 4 ? 1 : (mode == 8 ? 2 : 3))];
 }
 
 cudaError_t init_attn_frag() {
   for (int kind = 1; kind <= 2; ++kind)
-    for (int cross = 0; cross < 2; ++cross) {
-      cudaError_t e = cudaFuncSetAttribute(attn_frag_variant(kind, cross), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Z_SMEM_LIMIT);
+    for (int mode : {0, 4, 8, 16}) {
+      cudaError_t e = cudaFuncSetAttribute(attn_frag_variant(kind, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Z_SMEM_LIMIT);
       if (e != cudaSuccess) return e;
     }
   return cudaSuccess;
@@ -475,6 +525,7 @@ cudaError_t launch_attn_frag(const void* tmA, const void* tmB, const void* tmS, 
   const GemmAttnParams& a = p.a;
   if (a.M <= 0) return cudaSuccess;
   size_t smem = 0;
+  if (!p.fused) p.Cout = 0;
   if (!attn_frag_config(a.d, a.cross, p.Cout, &p.nst, &p.stage_bytes, &p.tmem_cols, &smem)) return cudaErrorInvalidValue;
   if (a.cross && !a.kvf_c) return cudaErrorInvalidValue;
   p.nacc = 2;
@@ -483,10 +534,10 @@ cudaError_t launch_attn_frag(const void* tmA, const void* tmB, const void* tmS, 
   const uint32_t fmt = kind == 1 ? 2u : 1u;
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(tc::Z_TM >> 4) << 24);
   const uint32_t idesc_o = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(tc::Z_TM >> 4) << 24);
-  const int nblk = (a.M + tc::Z_TM - 1) / tc::Z_TM;
+  const int nitems = ((a.M + tc::Z_TM - 1) / tc::Z_TM) * (p.fused ? 1 : a.heads);
   const int sms = attn_layer_sms();
-  const unsigned grid = (unsigned)(nblk < sms ? nblk : sms);
-  attn_frag_variant(kind, a.cross)<<<grid, tc::Z_THREADS, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(tmA),
+  const unsigned grid = (unsigned)(nitems < sms ? nitems : sms);
+  attn_frag_variant(kind, a.cross ? a.L : 0)<<<grid, tc::Z_THREADS, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(tmA),
                                                                      *reinterpret_cast<const CUtensorMap*>(tmB),
                                                                      *reinterpret_cast<const CUtensorMap*>(tmS),
                                                                      *reinterpret_cast<const CUtensorMap*>(tmW), p, idesc, idesc_o);

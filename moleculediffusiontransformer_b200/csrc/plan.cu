@@ -396,39 +396,45 @@ struct Builder {
     if (cross && !packed_cross) return false;
     return attn_layer_supported(pl.prec, C, L, pl.cfg.heads, pl.cfg.head_features, cross, C);
   }
-  bool frag_ok(int C, int L, int cross) const {
+  bool frag_ok(int C, int L, int cross, bool fused = true) const {
     const char* e = getenv("MDT_ATTN_FRAG");
     if (e && e[0] == '0') return false;
-    return attn_frag_supported(pl.prec, C, L, pl.cfg.heads, pl.cfg.head_features, cross, C);
+    if (!fused && getenv("MDT_NO_FRAG_UNFUSED")) return false;
+    return attn_frag_supported(pl.prec, C, L, pl.cfg.heads, pl.cfg.head_features, cross, fused ? C : 0);
   }
   void emit_attn_layer(std::vector<Op>& prog, const void* A, int C, int L, const float* dW32, const float* bias_q, int cross,
                        int cross_layer, const void* kn_flag, const void* kvf_c, const void* kvf_n, const float* dWo32,
-                       const float* bias_o, float* t, void* cop) {
+                       const float* bias_o, float* t, void* cop, bool fused = true) {
+    // fused == false: gemm_attn_frag.cu writes the head outputs to pl.att and the caller emits the out-projection GEMM itself
     Op op; op.type = OP_ATTN_LAYER; op.rps = L; op.cross = cross != 0; op.cross_layer = cross_layer;
     const int kch = pl.prec == MDT_PREC_TF32 ? 32 : 64;
     const int heads = pl.cfg.heads, d = pl.cfg.head_features, BN = cross ? d : 3 * d, Hd = heads * d;
     AttnLayerParams& y = op.al;
     GemmAttnParams& g = y.a;
     g.M = 0; g.heads = heads; g.d = d; g.kchunks = C / kch; g.C = C; g.L = L; g.Sb = 128 / L; g.cross = cross;
-    g.bias = bias_q; g.scale = 1.0f / sqrtf((float)d); g.att = nullptr; g.ldo = 0;
+    g.bias = bias_q; g.scale = 1.0f / sqrtf((float)d); g.att = fused ? nullptr : (void*)pl.att; g.ldo = fused ? 0 : Hd;
     g.kc = nullptr; g.kn = kn_flag; g.ldkv = 2 * Hd; g.kv_sample_stride = 0; g.n_cond = 0; g.nk = L; g.kv_fp32 = 1;
     g.kvf_c = kvf_c; g.kvf_n = kvf_n;
     const char* ps = getenv("MDT_PACK_SELF");
     g.pack_self = (!cross && L >= 2 && L <= 8 && !(ps && ps[0] == '0')) ? 1 : 0;
-    y.Cout = C; y.bias_o = bias_o; y.res = t; y.ldres = C; y.C32 = t; y.ldc = C; y.Cop = cop; y.ldcop = C;
-    if (!pl.attn_scratch) {
+    y.Cout = C; y.bias_o = bias_o; y.res = t; y.ldres = C; y.C32 = t; y.ldc = C; y.Cop = cop; y.ldcop = C; y.fused = fused ? 1 : 0;
+    if (fused && !pl.attn_scratch) {
       const size_t bytes = attn_layer_scratch_bytes(pl.prec, heads, d);
       pl.attn_scratch = dalloc((bytes + 3) / 4);
       CK(cudaMemset(pl.attn_scratch, 0, bytes));
     }
     y.scratch = pl.attn_scratch;
     const void* wop = tc_copy(dW32, (size_t)heads * BN * C);
-    const void* woo = tc_copy(dWo32, (size_t)C * Hd);
     if (make_tmap_act(op.tmA, A, pl.prec, C, L, (long long)pl.Beff_max) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(layer activation) failed");
     if (make_tmap_weight(op.tmB, wop, pl.prec, (long long)C, heads * BN, BN) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(layer weight) failed");
-    if (make_tmap_act(op.tmC, pl.attn_scratch, pl.prec, d, attn_layer_slots(heads) * 128, (long long)attn_layer_sms()) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(layer scratch) failed");
-    if (make_tmap_weight(op.tmD, woo, pl.prec, (long long)Hd, C, C) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(layer out-projection) failed");
-    op.frag = frag_ok(C, L, cross);
+    if (fused) {
+      const void* woo = tc_copy(dWo32, (size_t)C * Hd);
+      if (make_tmap_act(op.tmC, pl.attn_scratch, pl.prec, d, attn_layer_slots(heads) * 128, (long long)attn_layer_sms()) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(layer scratch) failed");
+      if (make_tmap_weight(op.tmD, woo, pl.prec, (long long)Hd, C, C) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(layer out-projection) failed");
+    } else {
+      memset(op.tmC, 0, sizeof op.tmC); memset(op.tmD, 0, sizeof op.tmD);
+    }
+    op.frag = fused ? frag_ok(C, L, cross) : true;
     if (cross && cross_layer >= 0) pl.cross[cross_layer].kperm = op.frag ? 1 : 0;
     emit(prog, op);
   }
@@ -599,7 +605,11 @@ struct Builder {
           d_bq_self = upload(b.data(), Hd);      // q bias only (see gemm_attn.cu)
           if (!tn_is_ln) emit_ln_apply(prog, t, C, L, tn);
           layer_self = layer_ok(C, L, 0, false);
-          if (!layer_self) emit_gemm_attn(prog, tn, C, L, d_wr_self, d_bq_self, 0, -1, nullptr, nullptr);
+          if (!layer_self) {
+            // wider levels: the per-(row block, head) variant of the TMEM-fragment kernel where it applies, else gemm_attn.cu
+            if (frag_ok(C, L, 0, false)) emit_attn_layer(prog, tn, C, L, d_wr_self, d_bq_self, 0, -1, nullptr, nullptr, nullptr, nullptr, nullptr, t, nullptr, false);
+            else emit_gemm_attn(prog, tn, C, L, d_wr_self, d_bq_self, 0, -1, nullptr, nullptr);
+          }
         } else if (fast) {
           if (!tn_is_ln) emit_ln_apply(prog, t, C, L, tn);
           emit_gemm_tma(prog, tn, C, L, 1, d_w, d_b, 3 * Hd, 0, nullptr, nullptr, pl.qkv);
@@ -675,6 +685,9 @@ struct Builder {
         const bool layer_cross = fuse_cross && layer_ok(C, L, 1, packed);
         if (layer_cross) {
           emit_ln_apply(prog, t, C, L, tn);
+        } else if (fuse_cross && packed && frag_ok(C, L, 1, false)) {
+          emit_ln_apply(prog, t, C, L, tn);
+          emit_attn_layer(prog, tn, C, L, d_wq, d_bq, 1, layer, cl.kv_null, cl.kvf_cond, cl.kvf_null, nullptr, nullptr, t, nullptr, false);
         } else if (fuse_cross) {
           emit_ln_apply(prog, t, C, L, tn);
           // row-major variant: the fused kernel streams fp32 K/V with cp.async in both tensor-core modes (tf32: rounded copy, bf16: the
@@ -1026,7 +1039,7 @@ static std::string describe(const Op& op, int Beff) {
     case OP_GEMM_TMA: snprintf(b, sizeof b, "gemm_tma  M=%d N=%d K=%dx%d L=%d bn=%d%s%s%s%s", Beff * op.rps, op.tg.N, op.tg.taps, op.tg.C, op.tg.L, op.tg.BN,
                                op.tg.gn_L ? " +gn" : "", op.tg.res ? " +res" : "", op.tg.act ? " +act" : "", h); break;
     case OP_GEMM_ATTN: snprintf(b, sizeof b, "gemm_attn%s %s M=%d C=%d L=%d%s", op.umma_core ? "_umma" : "", op.cross ? "cross" : "self", Beff * op.rps, op.gat.C, op.gat.L, h); break;
-    case OP_ATTN_LAYER: snprintf(b, sizeof b, "attn_%s %s M=%d C=%d L=%d%s%s", op.frag ? "frag " : "layer", op.cross ? "cross" : "self", Beff * op.rps, op.al.a.C, op.al.a.L, op.al.Cop ? " +cop" : "", h); break;
+    case OP_ATTN_LAYER: snprintf(b, sizeof b, "attn_%s%s %s M=%d C=%d L=%d%s%s", op.frag ? "frag " : "layer", op.al.fused ? "" : "(unfused)", op.cross ? "cross" : "self", Beff * op.rps, op.al.a.C, op.al.a.L, op.al.Cop ? " +cop" : "", h); break;
     case OP_GEMM: snprintf(b, sizeof b, "gemm      M=%d N=%d K=%d taps=%d stride=%d%s", Beff * op.rps, op.g.N, op.g.K, op.g.a.taps, op.g.a.stride, h); break;
     case OP_GN_APPLY: snprintf(b, sizeof b, "gn_apply  B=%d L=%d C=%d%s%s", Beff, op.ga.L, op.ga.c0 + op.ga.c1, op.ga.raw ? " +raw" : "", h); break;
     case OP_LN_APPLY: snprintf(b, sizeof b, "ln_apply  rows=%d C=%d%s", Beff * op.rps, op.la.C, h); break;
