@@ -148,8 +148,8 @@ int mdt_plan_set_context_mode(mdt_plan* plan, int pre_encoded);
  * 1: KarrasSampler (diffusion.py:399-453): rows carry sigma = sigma_hat, sigma_mid = sigma_next, dt_mid = sigma_next - sigma_hat,
  * dt_down = 0.5 (sigma - sigma_hat) and sigma_up = the noise scale sqrt(sigma_hat^2 - sigma^2) s_noise of the NEXT step; the second
  * update is x_hat + dt_down (d + d'), the step noise of iteration i is drawn ahead of its first denoiser call (slot i of
- * step_noise_dev / Philox stream i + 1) and `init_noise_scale` is the scale of step 0. */
-int mdt_plan_set_sampler_mode(mdt_plan* plan, int mode, float init_noise_scale);
+ * step_noise_dev / Philox stream i + 1) `init_noise_scale` is the scale of step 0 and `init_sigma` = sigmas[0] (x = sigmas[0] * noise, diffusion.py:438; row 0 carries sigma_hat). */
+int mdt_plan_set_sampler_mode(mdt_plan* plan, int mode, float init_noise_scale, float init_sigma);
 
 /* Inpainting: replaces QMDiffusion.inpaint -> XDiffusion_x.inpaint -> DiffusionInpainter.forward ->
  * ADPM2Sampler.inpaint (generative.py:871-914, diffusion.py:744-767, 612-625, 526-549).

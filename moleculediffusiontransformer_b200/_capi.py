@@ -80,7 +80,7 @@ def load() -> C.CDLL:
     lib.mdt_plan_inpaint.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, u64, u64, i64, f32, vp, vp]
     lib.mdt_plan_unet_forward.argtypes = [vp, vp, f32, vp, i32, i64, f32, vp, vp]
     lib.mdt_plan_set_context_mode.argtypes = [vp, C.c_int]
-    lib.mdt_plan_set_sampler_mode.argtypes = [vp, C.c_int, f32]
+    lib.mdt_plan_set_sampler_mode.argtypes = [vp, C.c_int, f32, f32]
     lib.mdt_plan_enable_taps.argtypes = [vp, C.c_int]
     lib.mdt_plan_read_tap.argtypes = [vp, C.c_char_p, vp, i64]
     lib.mdt_plan_read_tap.restype = i64

@@ -609,11 +609,12 @@ __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsign
 // One CTA per sample; injected noise arrives in the reference's (B,P,L) layout and is transposed via smem.
 __global__ void step_init_kernel(const float* __restrict__ noise0, float* __restrict__ x, float* __restrict__ xin,
                                  const IterScalars* __restrict__ iters, unsigned long long seed,
-                                 unsigned long long sample_offset, int B, int P, int L, int cfg) {
+                                 unsigned long long sample_offset, int B, int P, int L, int cfg, float sigma0) {
   extern __shared__ float tile[];  // [P][L+1]
   const int b = blockIdx.x;
   const int n = P * L;
-  const IterScalars it = iters[0];
+  IterScalars it = iters[0];
+  if (sigma0 >= 0.f) it.sigma = sigma0;
   if (noise0) {
     for (int e = threadIdx.x; e < n; e += blockDim.x) { const int pp = e / L, l = e - pp * L; tile[pp * (L + 1) + l] = noise0[(size_t)b * n + e]; }
     __syncthreads();
@@ -639,12 +640,12 @@ __global__ void step_init_kernel(const float* __restrict__ noise0, float* __rest
 
 cudaError_t launch_step_init(const float* noise0, float* x, float* xin, const IterScalars* iters,
                              unsigned long long seed, unsigned long long sample_offset, int B, int P, int L,
-                             int cfg, cudaStream_t s) {
+                             int cfg, float sigma0, cudaStream_t s) {
   if (B <= 0) return cudaSuccess;
   if ((P * L) % 4) return cudaErrorInvalidValue;
   const size_t smem = noise0 ? (size_t)P * (L + 1) * sizeof(float) : 0;
   if (smem > MDT_STEP_SMEM_MAX) return cudaErrorInvalidValue;
-  step_init_kernel<<<B, 256, smem, s>>>(noise0, x, xin, iters, seed, sample_offset, B, P, L, cfg);
+  step_init_kernel<<<B, 256, smem, s>>>(noise0, x, xin, iters, seed, sample_offset, B, P, L, cfg, sigma0);
   return cudaGetLastError();
 }
 

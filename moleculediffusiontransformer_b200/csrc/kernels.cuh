@@ -143,7 +143,7 @@ cudaError_t launch_film_fold(const float* ss, const float* gamma, const float* b
                              cudaStream_t s);
 cudaError_t launch_step_init(const float* noise0, float* x, float* xin, const IterScalars* iters,
                              unsigned long long seed, unsigned long long sample_offset, int B, int P, int L,
-                             int cfg, cudaStream_t s);
+                             int cfg, float sigma0, cudaStream_t s);   // sigma0 >= 0 overrides iters[0].sigma
 cudaError_t launch_step_update(int which, const StepParams& p, cudaStream_t s);
 // KarrasSampler step 0: x += scale * eps_0 (injected (B,P,L) tensor or Philox stream 1), xin = c_in * x (both branches)
 cudaError_t launch_karras_prenoise(float* x, float* xin, const float* noise, float scale, float c_in, unsigned long long seed,
@@ -280,6 +280,24 @@ cudaError_t init_ff_chain();
 // tmA: activation map; tmB0: W0 [mid][C] with a (KCH x 128) box; tmS: scratch viewed as [SMs][2 * 128][mid]; tmW: W2 [C][mid], (KCH x C) box
 cudaError_t launch_ff_chain(const void* tmA, const void* tmB0, const void* tmS, const void* tmW, const FFChainParams& p, int kind,
                             cudaStream_t s);
+
+// ---- whole Patcher / Unpatcher resnet at level 0 for few channels (resnet_small.cu) ---------------------------------------
+struct ResnetSmallParams {
+  const float* x; int Cin;          // input [B * L][Cin] fp32 token-major
+  int L, Cout;
+  const float* aff1;                // [2 * Cin] gamma | beta of block1.groupnorm (one group)
+  const float* w1; const float* b1; // conv1 packed [Cout][3 * Cin] (k = tap * Cin + ci), [Cout]
+  const float* ws; const float* bs; // 1x1 skip projection [Cout][Cin], [Cout]; null = identity (Cin == Cout)
+  const float* aff2; int aff2_stride; const int* call_idx;   // block2.groupnorm affine with FiLM folded in, per denoiser call
+  const float* w2; const float* b2; // conv2 packed [Cout][3 * Cout], [Cout]    (mode 0)
+  float* out;                       // mode 0: block output [B * L][Cout] fp32; mode 1: the skip / residual term, same shape
+  void* a2op; int kind;             // mode 1: SiLU(FiLM(GN(h1))) in the operand dtype (1 tf32, 2 bf16) for the conv2 GEMM
+  int B; int mode;                  // 0: whole block; 1: up to the input of conv2
+  float eps;
+};
+bool resnet_small_supported(int L, int Cin, int Cout, int groups, bool proj, int mode);
+cudaError_t init_resnet_small();
+cudaError_t launch_resnet_small(const ResnetSmallParams& p, cudaStream_t s);
 
 // ---- tensor-core GEMM (gemm_tc.cu) --------------------------------------------------------------
 // kind: 1 = tf32, 2 = bf16.  Wtc must hold the weights pre-converted by convert_weights_tc().

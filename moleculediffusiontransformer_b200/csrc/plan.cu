@@ -57,7 +57,7 @@ struct MdtError {
 // ------------------------------------------------------------------------------------------------
 // program representation
 // ------------------------------------------------------------------------------------------------
-enum OpType { OP_GEMM, OP_GN_STATS, OP_ROW_STATS, OP_ATTN, OP_UPGATHER, OP_PERMUTE, OP_GN_APPLY, OP_LN_APPLY, OP_GEMM_TMA, OP_GEMM_ATTN, OP_DUP_ROWS, OP_GEMM_FF, OP_ATTN_LAYER };
+enum OpType { OP_GEMM, OP_GN_STATS, OP_ROW_STATS, OP_ATTN, OP_UPGATHER, OP_PERMUTE, OP_GN_APPLY, OP_LN_APPLY, OP_GEMM_TMA, OP_GEMM_ATTN, OP_DUP_ROWS, OP_GEMM_FF, OP_ATTN_LAYER, OP_RESNET_SMALL };
 
 struct Op {
   OpType type = OP_GEMM;
@@ -72,6 +72,7 @@ struct Op {
   GemmAttnParams gat{};
   FFChainParams ffc{};
   AttnLayerParams al{};
+  ResnetSmallParams rs{};
   alignas(64) unsigned char tmA[128];
   alignas(64) unsigned char tmB[128];
   alignas(64) unsigned char tmC[128];
@@ -157,7 +158,7 @@ struct mdt_plan {
   cudaEvent_t staged = nullptr;    // the pinned staging tables of the previous call have been copied to the device
   bool ctx_pre_encoded = false;    // cond_dev holds the encoded embedding [B, n_ctx, F] (XDiffusion_x.sample(embedding=...))
   int sampler_mode = 0;            // 0: ADPM2 / AEuler rows, 1: KarrasSampler rows (mdt_plan_set_sampler_mode)
-  float init_noise_scale = 0.f;
+  float init_noise_scale = 0.f, init_sigma = 0.f;
   float* daux = nullptr;           // slope of denoiser call A (KarrasSampler)
   int n_ctx_cur = 0;
   // graph cache: key (Bc, n_ctx, cfg, has_step_noise, n_iters, single_call); everything else is device resident
@@ -456,6 +457,45 @@ struct Builder {
     const bool ok1 = tma_ok(Cin, L, Cout) && gn_apply_supported(L, Cin, groups);
     const bool ok2 = tma_ok(Cout, L, Cout) && gn_apply_supported(L, Cout, groups);
     const bool proj = has(pre + "to_out.weight");
+    // Patcher / Unpatcher resnets with few channels (resnet_small.cu): the whole block in one kernel when the second conv is small
+    // too (to_out), or everything up to the tensor-core conv2 (to_in) -- instead of GroupNorm passes and sliver-of-a-tile GEMMs
+    const bool small_on = tma() && in.c1 == 0 && groups == 1 && !getenv("MDT_NO_RESNET_SMALL");
+    const bool small_full = small_on && !out_op && Cout <= 32 && getenv("MDT_RESNET_SMALL_FULL") && resnet_small_supported(L, Cin, Cout, groups, proj, 0);
+    const bool small_head = small_on && !small_full && ok2 && Cin <= 32 && resnet_small_supported(L, Cin, Cout, groups, proj, 1);
+    if (small_full || small_head) {
+      Film f{};
+      f.w_ss = upload(T(pre + "to_scale_shift.to_scale_shift.1.weight", (int64_t)2 * Cout * M), (size_t)2 * Cout * M);
+      f.b_ss = upload(T(pre + "to_scale_shift.to_scale_shift.1.bias", 2 * Cout), 2 * Cout);
+      f.gamma = upload(T(pre + "block2.groupnorm.weight", Cout), Cout);
+      f.beta = upload(T(pre + "block2.groupnorm.bias", Cout), Cout);
+      f.C = Cout;
+      f.ss = dalloc((size_t)pl.max_calls * 2 * Cout);
+      f.aff = dalloc((size_t)pl.max_calls * 2 * Cout);
+      pl.films.push_back(f);
+      auto w2 = pack_conv(T(pre + "block2.project.weight", (int64_t)Cout * Cout * 3), Cout, Cout, 3);
+      const float* d_w2 = upload(w2);
+      const float* d_b2 = upload(T(pre + "block2.project.bias", Cout), Cout);
+      float* out = forced_out ? forced_out : acquire();
+      Op op; op.type = OP_RESNET_SMALL;
+      ResnetSmallParams& r = op.rs;
+      r.x = in.p0; r.Cin = Cin; r.L = L; r.Cout = Cout; r.aff1 = d_aff1; r.w1 = d_w1; r.b1 = d_b1;
+      r.ws = nullptr; r.bs = nullptr;
+      if (proj) {
+        r.ws = upload(T(pre + "to_out.weight", (int64_t)Cout * Cin), (size_t)Cout * Cin);
+        r.bs = upload(T(pre + "to_out.bias", Cout), Cout);
+      }
+      r.aff2 = f.aff; r.aff2_stride = 2 * Cout; r.call_idx = pl.d_call; r.w2 = d_w2; r.b2 = d_b2; r.out = out;
+      r.a2op = nullptr; r.kind = pl.prec; r.B = 0; r.mode = small_full ? 0 : 1; r.eps = 1e-5f;
+      if (small_full) { emit(prog, op); return out; }
+      float* a2f = acquire();
+      op.rs.a2op = a2f;
+      emit(prog, op);
+      void* oc = nullptr;
+      if (out_op) { oc = acquire(); *out_op = oc; }
+      emit_gemm_tma(prog, a2f, Cout, L, 3, d_w2, d_b2, Cout, 0, out, out, oc);
+      release(a2f);
+      return out;
+    }
     // block2's GroupNorm + FiLM + SiLU can run inside conv1's epilogue when a 32-row x 32-column epilogue block holds
     // whole (sample, group) sets: then h1 never goes to HBM and the separate normalisation pass disappears
     const int cpg2 = Cout / groups;
@@ -1040,6 +1080,7 @@ static std::string describe(const Op& op, int Beff) {
                                op.tg.gn_L ? " +gn" : "", op.tg.res ? " +res" : "", op.tg.act ? " +act" : "", h); break;
     case OP_GEMM_ATTN: snprintf(b, sizeof b, "gemm_attn%s %s M=%d C=%d L=%d%s", op.umma_core ? "_umma" : "", op.cross ? "cross" : "self", Beff * op.rps, op.gat.C, op.gat.L, h); break;
     case OP_ATTN_LAYER: snprintf(b, sizeof b, "attn_%s%s %s M=%d C=%d L=%d%s%s", op.frag ? "frag " : "layer", op.al.fused ? "" : "(unfused)", op.cross ? "cross" : "self", Beff * op.rps, op.al.a.C, op.al.a.L, op.al.Cop ? " +cop" : "", h); break;
+    case OP_RESNET_SMALL: snprintf(b, sizeof b, "resnet_small %s B=%d L=%d %d->%d%s", op.rs.mode ? "head" : "full", Beff, op.rs.L, op.rs.Cin, op.rs.Cout, h); break;
     case OP_GEMM: snprintf(b, sizeof b, "gemm      M=%d N=%d K=%d taps=%d stride=%d%s", Beff * op.rps, op.g.N, op.g.K, op.g.a.taps, op.g.a.stride, h); break;
     case OP_GN_APPLY: snprintf(b, sizeof b, "gn_apply  B=%d L=%d C=%d%s%s", Beff, op.ga.L, op.ga.c0 + op.ga.c1, op.ga.raw ? " +raw" : "", h); break;
     case OP_LN_APPLY: snprintf(b, sizeof b, "ln_apply  rows=%d C=%d%s", Beff * op.rps, op.la.C, h); break;
@@ -1110,6 +1151,7 @@ static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_con
                    : launch_attn_layer(op.tmA, op.tmB, op.tmC, op.tmD, y, pl.prec, s));
         pl.launches++; break;
       }
+      case OP_RESNET_SMALL: { ResnetSmallParams r = op.rs; r.B = Beff; CK(launch_resnet_small(r, s)); pl.launches++; break; }
       case OP_GEMM_FF: {
         FFChainParams g = op.ffc; g.M = Beff * op.rps; g.rev = rev;
         CK(launch_ff_chain(op.tmA, op.tmB, op.tmC, op.tmD, g, pl.prec, s)); pl.launches++; break;
@@ -1303,6 +1345,7 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
     CK(init_gemm_attn_umma());
     CK(init_attn_layer());
     CK(init_attn_frag());
+    CK(init_resnet_small());
     CK(init_ff_chain());
     pl->cfg = *cfg; pl->device = device; pl->prec = cfg->precision;
     pl->P = cfg->in_channels; pl->L0 = cfg->length; pl->Hd = cfg->heads * cfg->head_features; pl->F = cfg->ctx_features;
@@ -1367,11 +1410,12 @@ void mdt_plan_destroy(mdt_plan* pl) {
 int64_t mdt_plan_device_bytes(const mdt_plan* pl) { return pl ? (int64_t)(pl->wcap + pl->act_bytes) : 0; }
 int64_t mdt_plan_launch_count(const mdt_plan* pl) { return pl ? pl->launches : 0; }
 
-int mdt_plan_set_sampler_mode(mdt_plan* pl, int mode, float init_noise_scale) {
+int mdt_plan_set_sampler_mode(mdt_plan* pl, int mode, float init_noise_scale, float init_sigma) {
   if (!pl) return fail(MDT_ERR_INVALID, "null plan");
   if (mode != 0 && mode != 1) return fail(MDT_ERR_INVALID, "unknown sampler mode %d", mode);
   pl->sampler_mode = mode;
   pl->init_noise_scale = init_noise_scale;
+  pl->init_sigma = init_sigma;
   return 0;
 }
 
@@ -1495,8 +1539,9 @@ int mdt_plan_sample(mdt_plan* pl, const float* cond_dev, int32_t n_ctx, const fl
       const int Bc = (int)std::min<int64_t>(pl->Bmax, B - b0);
       const int Beff = cfg ? 2 * Bc : Bc;
       run_context(*pl, cond_dev + (size_t)b0 * n_ctx * (pl->ctx_pre_encoded ? pl->F : 1), Bc, n_ctx, cfg, s);
+      // KarrasSampler: x = sigmas[0] * noise while row 0 carries sigma_hat_0 (the x_hat / network input follow in karras_prenoise)
       CK(launch_step_init(noise0_dev ? noise0_dev + (size_t)b0 * per : nullptr, pl->x, pl->xin, pl->d_iters, seed,
-                          sample_offset + (uint64_t)b0, Bc, P, L, cfg ? 1 : 0, s));
+                          sample_offset + (uint64_t)b0, Bc, P, L, cfg ? 1 : 0, karras ? pl->init_sigma : -1.0f, s));
       CK(launch_set_int(pl->d_call, 0, s));
       pl->launches += 2;
       if (karras) {   // x_hat of step 0: the first step noise goes in ahead of the first denoiser call (diffusion.py:425-426)

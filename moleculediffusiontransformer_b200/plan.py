@@ -150,10 +150,11 @@ class SamplerPlan:
             tokens = torch.empty((b, L), dtype=torch.uint8, device=self.device) if return_tokens else None
             _capi.check(self.lib.mdt_plan_set_context_mode(self.handle, int(bool(pre_encoded))))
             if isinstance(sampler, KarrasSampler):
-                s0 = karras_noise_scales(sigma_schedule(num_steps, "cpu"), num_steps, sampler)[0]
-                _capi.check(self.lib.mdt_plan_set_sampler_mode(self.handle, 1, float(s0)))
+                sig = sigma_schedule(num_steps, "cpu")
+                s0 = karras_noise_scales(sig, num_steps, sampler)[0]
+                _capi.check(self.lib.mdt_plan_set_sampler_mode(self.handle, 1, float(s0), float(sig[0])))
             else:
-                _capi.check(self.lib.mdt_plan_set_sampler_mode(self.handle, 0, 0.0))
+                _capi.check(self.lib.mdt_plan_set_sampler_mode(self.handle, 0, 0.0, 0.0))
             _capi.check(self.lib.mdt_plan_sample(
                 self.handle, cond.data_ptr(), n_ctx, n0.data_ptr() if n0 is not None else None,
                 sn.data_ptr() if sn is not None else None, table.ctypes.data, table.shape[0],
