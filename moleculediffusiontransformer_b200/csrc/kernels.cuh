@@ -294,6 +294,7 @@ struct ResnetSmallParams {
   void* a2op; int kind;             // mode 1: SiLU(FiLM(GN(h1))) in the operand dtype (1 tf32, 2 bf16) for the conv2 GEMM
   int B; int mode;                  // 0: whole block; 1: up to the input of conv2
   float eps;
+  int split1, split2;               // run conv1 + skip / conv2 as 3xTF32 (hi/lo operand split: fp32-grade) instead of one tf32 pass
 };
 bool resnet_small_supported(int L, int Cin, int Cout, int groups, bool proj, int mode);
 cudaError_t init_resnet_small();

@@ -460,7 +460,7 @@ struct Builder {
     // Patcher / Unpatcher resnets with few channels (resnet_small.cu): the whole block in one kernel when the second conv is small
     // too (to_out), or everything up to the tensor-core conv2 (to_in) -- instead of GroupNorm passes and sliver-of-a-tile GEMMs
     const bool small_on = tma() && in.c1 == 0 && groups == 1 && !getenv("MDT_NO_RESNET_SMALL");
-    const bool small_full = small_on && !out_op && Cout <= 32 && getenv("MDT_RESNET_SMALL_FULL") && resnet_small_supported(L, Cin, Cout, groups, proj, 0);
+    const bool small_full = small_on && !out_op && Cout <= 32 && resnet_small_supported(L, Cin, Cout, groups, proj, 0);
     const bool small_head = small_on && !small_full && ok2 && Cin <= 32 && resnet_small_supported(L, Cin, Cout, groups, proj, 1);
     if (small_full || small_head) {
       Film f{};
@@ -486,6 +486,9 @@ struct Builder {
       }
       r.aff2 = f.aff; r.aff2_stride = 2 * Cout; r.call_idx = pl.d_call; r.w2 = d_w2; r.b2 = d_b2; r.out = out;
       r.a2op = nullptr; r.kind = pl.prec; r.B = 0; r.mode = small_full ? 0 : 1; r.eps = 1e-5f;
+      // 3xTF32 where the rounding would land straight on the sampler state: the first conv of the network input (to_in) and the last
+      // conv of the network output (to_out); to_out's first conv / skip keep the single tf32 pass they had as TMA GEMMs
+      r.split1 = small_full ? 0 : 1; r.split2 = 1;
       if (small_full) { emit(prog, op); return out; }
       float* a2f = acquire();
       op.rs.a2op = a2f;
