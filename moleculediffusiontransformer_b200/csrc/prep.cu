@@ -4,6 +4,7 @@
 //              One CTA owns whole samples, so statistics never leave shared memory.
 //   ln_apply : LayerNorm (no affine: gamma/beta are folded into the following projection) per row.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "aload.cuh"
 #include "tc_common.cuh"
 
@@ -17,6 +18,10 @@ __device__ __forceinline__ void store_op4(void* base, size_t idx, float4 v) {
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = make_uint2(tc::pack_bf16(v.x, v.y), tc::pack_bf16(v.z, v.w));
   }
 }
+
+// SiLU with ex2.approx / rcp.approx (~2 ulp each): these kernels only feed tf32 / bf16 MMA operands (rounded to 11 / 8 bits right
+// after), and the precise expf + division form was a third of their issue slots (ncu: issue-active 36 %, DRAM 33 %)
+__device__ __forceinline__ float silu_op(float v) { return v * __fdividef(1.0f, 1.0f + __expf(-v)); }
 
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p, co
       const float4 h = __ldg(reinterpret_cast<const float4*>(aff + C + c));
       v.x = v.x * g.x + h.x; v.y = v.y * g.y + h.y; v.z = v.z * g.z + h.z; v.w = v.w * g.w + h.w;
     }
-    if (p.silu) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+    if (p.silu) { v.x = silu_op(v.x); v.y = silu_op(v.y); v.z = silu_op(v.z); v.w = silu_op(v.w); }
     store_op4<KIND>(p.out, gidx, v);
   }
 }
@@ -178,10 +183,95 @@ __global__ void __launch_bounds__(256) gn_apply_reg_kernel(const GnApplyParams p
         const float4 ha = __ldg(reinterpret_cast<const float4*>(aff + C + c));
         x.x = x.x * ga.x + ha.x; x.y = x.y * ga.y + ha.y; x.z = x.z * ga.z + ha.z; x.w = x.w * ga.w + ha.w;
       }
-      if (p.silu) { x.x = silu_f(x.x); x.y = silu_f(x.y); x.z = silu_f(x.z); x.w = silu_f(x.w); }
+      if (p.silu) { x.x = silu_op(x.x); x.y = silu_op(x.y); x.z = silu_op(x.z); x.w = silu_op(x.w); }
       store_op4<KIND>(p.out, gidx, x);
     }
   }
+}
+
+// Slab variant for short samples (L <= 16): a warp owns (sample, 128-channel slab); lane = 4 channels, the L rows live in registers.
+// Every load / store instruction moves 512 contiguous bytes per row, all L rows of the item are in flight at once, and a warp walks
+// items grid-stride with the next item's loads issued before the current one is reduced.  Groups must not straddle a slab
+// (cpg | 128) and a slab must not straddle the two concatenated sources (c0 % 128 == 0).
+template <int KIND, int LMAX>
+__global__ void __launch_bounds__(256) gn_apply_slab_kernel(const GnApplyParams p) {
+  const int C = p.c0 + p.c1, L = p.L, cpg = C / p.groups;
+  const int lane = threadIdx.x & 31;
+  const int slabs = C >> 7;
+  const long long items = (long long)p.B * slabs;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int gl = cpg >> 2;                       // lanes per group (1 .. 32)
+  const float inv_n = 1.0f / (float)(cpg * L);
+  const float* aff = nullptr;
+  if (p.aff) aff = p.aff + (size_t)(p.call_idx ? *p.call_idx : 0) * p.aff_call_stride;
+  auto load_item = [&](long long item, float4 (&v)[LMAX]) {
+    const long long it2 = p.rev ? items - 1 - item : item;
+    const int b = (int)(it2 / slabs), c = (int)(it2 - (long long)b * slabs) * 128 + lane * 4;
+    const bool second = c >= p.c0;
+    const float* src = second ? p.src1 + (size_t)b * L * p.c1 + (c - p.c0) : p.src0 + (size_t)b * L * p.c0 + c;
+    const int ld = second ? p.c1 : p.c0;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < L) {
+        v[l] = __ldg(reinterpret_cast<const float4*>(src + (size_t)l * ld));
+        if (second) { v[l].x *= p.scale1; v[l].y *= p.scale1; v[l].z *= p.scale1; v[l].w *= p.scale1; }
+      }
+  };
+  constexpr bool PREFETCH = LMAX <= 8;           // 16 rows in registers twice over would cost the occupancy that hides the latency
+  float4 cur[LMAX], nxt[PREFETCH ? LMAX : 1];
+  if (PREFETCH && w < items) load_item(w, cur);
+  for (; w < items; w += nwarps) {
+    const bool more = PREFETCH && w + nwarps < items;
+    if constexpr (PREFETCH) { if (more) load_item(w + nwarps, nxt); }
+    else load_item(w, cur);
+    const long long it2 = p.rev ? items - 1 - w : w;
+    const int b = (int)(it2 / slabs), c = (int)(it2 - (long long)b * slabs) * 128 + lane * 4;
+    float sum = 0.f;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) if (l < L) sum += (cur[l].x + cur[l].y) + (cur[l].z + cur[l].w);
+    for (int o = gl >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_n;
+    float sq = 0.f;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < L) {
+        const float a = cur[l].x - mean, bb = cur[l].y - mean, cc = cur[l].z - mean, d = cur[l].w - mean;
+        sq = fmaf(a, a, sq); sq = fmaf(bb, bb, sq); sq = fmaf(cc, cc, sq); sq = fmaf(d, d, sq);
+      }
+    for (int o = gl >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = 1.0f / sqrtf(sq * inv_n + p.eps);
+    float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), ha = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (aff) { ga = __ldg(reinterpret_cast<const float4*>(aff + c)); ha = __ldg(reinterpret_cast<const float4*>(aff + C + c)); }
+    const size_t g0 = (size_t)b * L * C + c;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < L) {
+        float4 x = cur[l];
+        if (p.raw) store_op4<KIND>(p.raw, g0 + (size_t)l * C, x);
+        x.x = (x.x - mean) * rstd * ga.x + ha.x; x.y = (x.y - mean) * rstd * ga.y + ha.y;
+        x.z = (x.z - mean) * rstd * ga.z + ha.z; x.w = (x.w - mean) * rstd * ga.w + ha.w;
+        if (p.silu) { x.x = silu_op(x.x); x.y = silu_op(x.y); x.z = silu_op(x.z); x.w = silu_op(x.w); }
+        store_op4<KIND>(p.out, g0 + (size_t)l * C, x);
+      }
+    if constexpr (PREFETCH) {
+      if (more) {
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) cur[l] = nxt[l];
+      }
+    }
+  }
+}
+
+static bool gn_slab_ok(const GnApplyParams& p) {
+  const int C = p.c0 + p.c1;
+  if (p.L < 1 || p.L > 16 || (C & 127) || C % p.groups) return false;
+  const int cpg = C / p.groups;
+  if (cpg < 4 || cpg > 128 || (cpg & (cpg - 1)) || (128 % cpg)) return false;
+  if (p.c1 && (p.c0 & 127)) return false;
+  // measured (profiles/README.md, B = 8192): the slab mapping wins for short samples and single-slab rows (L = 4: 20 vs 34 us,
+  // L = 16 / C = 128: 45 vs 59 us) and loses where a lane would hold 16 rows of a two-slab sample (L = 16 / C = 256: 111 vs 91 us)
+  return p.L <= 8 || C <= 128;
 }
 
 static int gn_spc(int L, int C) {
@@ -200,6 +290,23 @@ bool gn_apply_supported(int L, int C, int groups) {
 cudaError_t launch_gn_apply(const GnApplyParams& p, int kind, cudaStream_t s) {
   if (p.B <= 0) return cudaSuccess;
   const int C = p.c0 + p.c1;
+  static const bool slab_off = getenv("MDT_NO_GN_SLAB") != nullptr;
+  if (!slab_off && gn_slab_ok(p)) {
+    static int sms = 0;
+    if (sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const long long items = (long long)p.B * (C >> 7);
+    const long long blocks_needed = (items + 7) / 8;
+    // two items per warp on average keeps the prefetch useful; cap at 8 resident blocks per SM
+    long long blocks = p.L <= 8 ? (blocks_needed + 1) / 2 : blocks_needed;
+    const long long cap = (long long)sms * 8;
+    if (p.L <= 8 && blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+#define MDT_SLAB_LAUNCH(K, LM) gn_apply_slab_kernel<K, LM><<<(unsigned)blocks, 256, 0, s>>>(p)
+    if (kind == 1) { if (p.L <= 4) MDT_SLAB_LAUNCH(1, 4); else if (p.L <= 8) MDT_SLAB_LAUNCH(1, 8); else MDT_SLAB_LAUNCH(1, 16); }
+    else { if (p.L <= 4) MDT_SLAB_LAUNCH(2, 4); else if (p.L <= 8) MDT_SLAB_LAUNCH(2, 8); else MDT_SLAB_LAUNCH(2, 16); }
+#undef MDT_SLAB_LAUNCH
+    return cudaGetLastError();
+  }
   {
     const int cpg = C / p.groups;
     const int pieces = p.L * cpg / 4;                    // float4 per (sample, group)
