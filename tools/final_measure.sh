@@ -1,10 +1,18 @@
 #!/bin/bash
-# One gpurun call: full GPU test suite, default bench (+ bf16), reference arm, ncu launch list, ncu --set full of the packed cross-attention launches.
+# One gpurun call (round 2): ncu launch list of one ADPM2 iteration, DRAM traffic of 1 and 2 iterations, ncu --set full of the
+# dominant kernels.  Everything lands in gpurun_out/ (summaries are copied to profiles/ by hand after reading them here).
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/ -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; cat gpurun_out/bench_default.json
-timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.json 2>/dev/null; cat gpurun_out/bench_reference.json
-MDT_GRAPH=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_tf32.csv python tools/profile_step.py tf32 4096 2 > gpurun_out/ncu1.log 2>&1
-python tools/summarize_launches.py gpurun_out/launches_tf32.csv 2>/dev/null | head -12
-MDT_GRAPH=0 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:gemm_attn_kernel<\(int\)1, \(int\)3>' -s 4 -c 3 -o gpurun_out/prof_gemm_attn_packed_cross -f python tools/profile_step.py tf32 4096 2 > gpurun_out/ncu2.log 2>&1
-ls -la gpurun_out/prof_gemm_attn_packed_cross.ncu-rep; tail -2 gpurun_out/ncu2.log
+MDT_GRAPH=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/r02_launches_tf32.csv python tools/profile_step.py tf32 4096 2 > gpurun_out/ncu_l.log 2>&1
+python tools/summarize_launches.py gpurun_out/r02_launches_tf32.csv > gpurun_out/r02_launches_tf32.summary.txt 2>&1; head -14 gpurun_out/r02_launches_tf32.summary.txt
+tools/measure_traffic.sh tf32 4096
+cap() {  # name regex skip count
+  MDT_GRAPH=0 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c $4 -o gpurun_out/r02_prof_$1 -f python tools/profile_step.py tf32 4096 2 > gpurun_out/ncu_$1.log 2>&1
+  ls -la gpurun_out/r02_prof_$1.ncu-rep 2>&1 | cut -c30-
+}
+cap attn_frag_self 'attn_frag_kernel<\(int\)1, \(int\)0>' 4 3
+cap attn_frag_cross 'attn_frag_kernel<\(int\)1, \(int\)16>' 2 2
+cap attn_frag_cross_l2 'attn_frag_kernel<\(int\)1, \(int\)4>' 2 2
+cap ff_chain 'ff_chain_kernel' 2 2
+cap gemm_tma 'gemm_tma_kernel' 20 12
+cap resnet_small 'resnet_small_kernel' 0 2
+cap step_update 'step_update_kernel' 0 2
