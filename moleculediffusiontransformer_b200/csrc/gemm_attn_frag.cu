@@ -86,15 +86,23 @@ __device__ __forceinline__ void add_q_bias(uint32_t (&qf)[16], const float* __re
   }
 }
 
+// hint != 0 (tf32 scratch slots): stores carry an L2 evict_last policy, the slot is read back by TMA within microseconds
 template <int OK>
-__device__ __forceinline__ void store_o_tiles(const float (&oc)[8][4], void* out, size_t out_base, int ldo, int rows_valid, int g, int q) {
+__device__ __forceinline__ void store_o_tiles(const float (&oc)[8][4], void* out, size_t out_base, int ldo, int rows_valid, int g, int q,
+                                              uint64_t hint = 0) {
   typedef SmemIO<OK> OUT;
   const bool ok0 = g < rows_valid, ok1 = g + 8 < rows_valid;
   const size_t o0 = out_base + (size_t)g * ldo + 2 * q, o1 = o0 + (size_t)8 * ldo;
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
-    if (ok0) OUT::st2(out, o0 + n * 8, oc[n][0], oc[n][1]);
-    if (ok1) OUT::st2(out, o1 + n * 8, oc[n][2], oc[n][3]);
+    if (OK == 1 && hint) {
+      uint32_t* ob = reinterpret_cast<uint32_t*>(out);
+      if (ok0) st_global_hint_b32x2(ob + o0 + n * 8, to_tf32(oc[n][0]), to_tf32(oc[n][1]), hint);
+      if (ok1) st_global_hint_b32x2(ob + o1 + n * 8, to_tf32(oc[n][2]), to_tf32(oc[n][3]), hint);
+    } else {
+      if (ok0) OUT::st2(out, o0 + n * 8, oc[n][0], oc[n][1]);
+      if (ok1) OUT::st2(out, o1 + n * 8, oc[n][2], oc[n][3]);
+    }
   }
 }
 
@@ -259,6 +267,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
     const size_t cta_slot0 = (size_t)blockIdx.x * p.nslot;
     const uint32_t lane_addr = (uint32_t)r16 << 16;
     const int sub = gp * 2 + half;          // this warp's column quarter of the OUT tile (four warps per quadrant)
+    const uint64_t l2pol = p.l2_hint ? l2_policy_evict_last() : 0;
 
     auto final_epilogue = [&](int kk) {
       const int m0 = block_of_k(kk) * Z_TM + qd * 32;      // first token row of this warp's quadrant
@@ -386,7 +395,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
               for (int n = 0; n < 8; ++n)
                 mma_tf32_16x8x8(oc[n], pa[t], __float_as_uint(v0[n * 8]), __float_as_uint(v0[Z_VLD + n * 8]));
             }
-            store_o_tiles<KIND>(oc, obuf, ob, ldo, rows_valid, g, q);
+            store_o_tiles<KIND>(oc, obuf, ob, ldo, rows_valid, g, q, fused ? l2pol : 0);
           }
           __syncwarp();                                     // the v tile is rewritten by the next head
         } else {
@@ -451,7 +460,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
                 }
               }
             }
-            store_o_tiles<KIND>(oc, obuf, ob, ldo, rows_valid, g, q);
+            store_o_tiles<KIND>(oc, obuf, ob, ldo, rows_valid, g, q, fused ? l2pol : 0);
           }
         }
         if (fused && h + 2 >= heads) {

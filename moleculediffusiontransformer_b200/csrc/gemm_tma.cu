@@ -11,6 +11,7 @@
 //              operand-dtype stores
 // Persistent, one CTA per SM: 4-stage smem ring, 16 epilogue warps, two TMEM accumulators so the epilogue of tile i overlaps tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include "aload.cuh"
 #include "tc_common.cuh"
@@ -27,6 +28,11 @@ constexpr int T_EPI_WARPS = 16;
 constexpr int T_STG_LD = 36;                                  // 32 columns + 4 floats of padding per staged row
 constexpr int T_STG_BYTES = T_EPI_WARPS * 32 * T_STG_LD * 4;  // per-warp private staging, 4.5 KB each
 constexpr int T_SMEM_BYTES = T_STAGES * T_STAGE_BYTES + T_STG_BYTES + 1024;
+// BN = 256 (one n-tile for the 256-wide levels: the activation tile is streamed once per row block instead of twice, -25 % L2 -> SM
+// operand bytes): 48 KB stages, three of them
+constexpr int T_STAGES_WIDE = 3;
+constexpr int T_STAGE_BYTES_WIDE = T_A_BYTES + 256 * 128;
+constexpr int T_SMEM_BYTES_WIDE = T_STAGES_WIDE * T_STAGE_BYTES_WIDE + T_STG_BYTES + 1024;
 constexpr int T_THREADS = 64 + 32 * T_EPI_WARPS;
 
 // Persistent kernel: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... with the N tile index
@@ -55,8 +61,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
   const int m_tiles = (p.M + T_TM - 1) / T_TM;
   const int total_tiles = m_tiles * n_tiles;
   const int num_chunks = p.taps * p.kchunks;
+  const int NST = BN > 128 ? T_STAGES_WIDE : T_STAGES;
+  const int stage_bytes = BN > 128 ? T_STAGE_BYTES_WIDE : T_STAGE_BYTES;
   // two accumulators; narrow tiles still read 32 columns per tcgen05.ld, so keep 32 columns of slack
-  const uint32_t tmem_cols = BN <= 32 ? 64u : (BN <= 64 ? 128u : 256u);
+  const uint32_t tmem_cols = BN <= 32 ? 64u : (BN <= 64 ? 128u : (BN <= 128 ? 256u : 512u));
 
   if (tid == 0) {
     for (int s = 0; s < T_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -74,7 +82,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const uint32_t tx = (uint32_t)(T_A_BYTES + BN * 128);
-      int c = 0;
+      int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int te = p.rev ? total_tiles - 1 - t : t;
         const int mt = te / n_tiles, nt = te - mt * n_tiles;
@@ -82,34 +90,32 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
         if (p.L >= T_TM) { const int tps = p.L / T_TM; b0 = mt / tps; l0 = (mt - b0 * tps) * T_TM; }
         else { b0 = mt * p.Sb; l0 = 0; }
         for (int tap = 0; tap < p.taps; ++tap) {
-          for (int kc = 0; kc < p.kchunks; ++kc, ++c) {
-            const int stage = c % T_STAGES;
-            const uint32_t phase = (uint32_t)(c / T_STAGES) & 1u;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
-            uint8_t* sa = smem + stage * T_STAGE_BYTES;
+            uint8_t* sa = smem + stage * stage_bytes;
             mbar_arrive_expect_tx(&full_bar[stage], tx);
             tma_load_3d(sa, &tmA, &full_bar[stage], kc * KCH, l0 + tap - p.pad, b0);
             tma_load_2d(sa + T_A_BYTES, &tmB, &full_bar[stage], tap * p.C + kc * KCH, nt * BN);
+            if (++stage == NST) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    int c = 0, it = 0;
+    int it = 0;
+    int stage = 0; uint32_t phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(&acc_empty[buf], aphase ^ 1u);      // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-      for (int k0 = 0; k0 < num_chunks; ++k0, ++c) {
-        const int stage = c % T_STAGES;
-        const uint32_t phase = (uint32_t)(c / T_STAGES) & 1u;
+      for (int k0 = 0; k0 < num_chunks; ++k0) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * T_STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + T_A_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -118,6 +124,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
           if (k0 == num_chunks - 1) umma_commit(&acc_full[buf]);
         }
         __syncwarp();
+        if (++stage == NST) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
     const int ew = warp - 2;             // 0..15
     const int q = warp & 3;              // TMEM lane quadrant this warp may access
     const int half = ew >> 2;            // column group (0..3) handled by this warp
-    float* stg = reinterpret_cast<float*>(smem + T_STAGES * T_STAGE_BYTES) + (size_t)ew * 32 * T_STG_LD;
+    float* stg = reinterpret_cast<float*>(smem + NST * stage_bytes) + (size_t)ew * 32 * T_STG_LD;
     // BN = 128: four groups of 32 columns; BN = 64: two groups; narrower tiles: one group
     const int ngroups = BN >= 128 ? 4 : (BN >= 64 ? 2 : 1);
     const int cols_per_half = BN / ngroups;
@@ -273,6 +280,8 @@ static EncodeTiledFn encode_fn() {
 }  // namespace tc
 
 int tma_pick_bn(int N) {
+  static const bool wide_off = getenv("MDT_NO_WIDE_BN") != nullptr;
+  if (N % 256 == 0 && !wide_off) return 256;
   if (N % 128 == 0) return 128;
   if (N % 64 == 0) return 64;
   if (N % 32 == 0) return 32;
@@ -318,9 +327,10 @@ int make_tmap_weight(void* map128, const void* base, int kind, long long K, int 
 }
 
 cudaError_t init_gemm_tma() {
-  cudaError_t e = cudaFuncSetAttribute(tc::gemm_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::T_SMEM_BYTES);
+  const int mx = tc::T_SMEM_BYTES_WIDE > tc::T_SMEM_BYTES ? tc::T_SMEM_BYTES_WIDE : tc::T_SMEM_BYTES;
+  cudaError_t e = cudaFuncSetAttribute(tc::gemm_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(tc::gemm_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::T_SMEM_BYTES);
+  return cudaFuncSetAttribute(tc::gemm_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
 }
 
 static int g_num_sms = 0;
@@ -340,8 +350,9 @@ cudaError_t launch_gemm_tma(const void* tmA, const void* tmB, const TmaGemmParam
   const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);   // persistent: one CTA per SM
   const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(tmA);
   const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(tmB);
-  if (kind == 1) tc::gemm_tma_kernel<1><<<grid, tc::T_THREADS, tc::T_SMEM_BYTES, s>>>(a, b, p, idesc);
-  else tc::gemm_tma_kernel<2><<<grid, tc::T_THREADS, tc::T_SMEM_BYTES, s>>>(a, b, p, idesc);
+  const int smem = p.BN > 128 ? tc::T_SMEM_BYTES_WIDE : tc::T_SMEM_BYTES;
+  if (kind == 1) tc::gemm_tma_kernel<1><<<grid, tc::T_THREADS, smem, s>>>(a, b, p, idesc);
+  else tc::gemm_tma_kernel<2><<<grid, tc::T_THREADS, smem, s>>>(a, b, p, idesc);
   return cudaGetLastError();
 }
 

@@ -239,6 +239,7 @@ struct AttnLayerParams {
   float* C32; int ldc;     // fp32 output
   void* Cop; int ldcop;    // operand-dtype copy of the output (the next GEMM's A operand) or null
   void* scratch;           // [SMs][attn_layer_slots(heads)][128][d] operand dtype: CTA-private head-output slots (L2 resident)
+  int l2_hint;             // scratch stores carry an L2 evict_last policy (MDT_L2_HINT=1; measured in profiles/README.md)
   int fused;               // 1: out-projection inside the kernel; 0 (gemm_attn_frag.cu only): head outputs go to a.att, one work item per (row block, head)
   int nslot;               // filled by the launcher from here on
   int nst, stage_bytes, nacc; unsigned tmem_cols;

@@ -419,6 +419,7 @@ struct Builder {
     const char* ps = getenv("MDT_PACK_SELF");
     g.pack_self = (!cross && L >= 2 && L <= 8 && !(ps && ps[0] == '0')) ? 1 : 0;
     y.Cout = C; y.bias_o = bias_o; y.res = t; y.ldres = C; y.C32 = t; y.ldc = C; y.Cop = cop; y.ldcop = C; y.fused = fused ? 1 : 0;
+    { const char* lh = getenv("MDT_L2_HINT"); y.l2_hint = (lh && lh[0] == '1') ? 1 : 0; }
     if (fused && !pl.attn_scratch) {
       const size_t bytes = attn_layer_scratch_bytes(pl.prec, heads, d);
       pl.attn_scratch = dalloc((bytes + 3) / 4);
@@ -502,7 +503,7 @@ struct Builder {
     // block2's GroupNorm + FiLM + SiLU can run inside conv1's epilogue when a 32-row x 32-column epilogue block holds
     // whole (sample, group) sets: then h1 never goes to HBM and the separate normalisation pass disappears
     const int cpg2 = Cout / groups;
-    const bool fuse_gn = ok1 && ok2 && !getenv("MDT_NO_FUSED_GN") && tma_pick_bn(Cout) == 128 && L <= 32 && (32 % L) == 0 &&
+    const bool fuse_gn = ok1 && ok2 && !getenv("MDT_NO_FUSED_GN") && tma_pick_bn(Cout) >= 128 && L <= 32 && (32 % L) == 0 &&
                          (cpg2 == 16 || cpg2 == 32);
     float* h1 = fuse_gn ? nullptr : acquire();
     float* a1 = nullptr; float* raw = nullptr; float* a2f = nullptr;

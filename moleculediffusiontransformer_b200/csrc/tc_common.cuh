@@ -134,6 +134,19 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 
+// ---- L2 residency hints for the CTA-private scratch (rewritten every block, read back by TMA a few microseconds later) ----------
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_global_hint_b32x2(void* addr, uint32_t a, uint32_t b, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(addr), "r"(a), "r"(b), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_global_hint_b32x4(void* addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol) : "memory");
+}
+
 // ---- TMA (cp.async.bulk.tensor) -----------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

@@ -233,3 +233,51 @@ def test_vocabulary_table_rejects_what_the_device_decoder_cannot_express():
         with pytest.raises(ValueError):
             vocabulary_table(bad)
     assert is_novel(["CCO"], "CCN") and not is_novel(["CCO"], "CCO")
+
+
+def test_empty_shard_and_plan_cache_housekeeping():
+    """A rank that shard_bounds leaves without rows must still return a [0, L] uint8 block for the gather (no CUDA call is made);
+    invalidate_plans() / the weights fingerprint exist for writes that bypass PyTorch's version counter."""
+    import torch
+    import moleculediffusiontransformer_b200 as mdt
+    from moleculediffusiontransformer_b200.launcher import model_runner, shard_bounds
+
+    torch.manual_seed(0)
+    m = mdt.QMDiffusion(max_length=64, pred_dim=16, channels=64, unet_type="cfg", context_embedding_max_length=12,
+                        pos_emb_fourier=True, pos_emb_fourier_add=False, text_embed_dim=64, embed_dim_position=64)
+    assert shard_bounds(1, 2, 1) == (1, 1)
+    tok = model_runner(m, "cpu", 5.0, 6, seed=1)(torch.zeros(0, 12), 1)
+    assert tok.shape == (0, 64) and tok.dtype == torch.uint8
+    f0 = m._weights_fingerprint()
+    with torch.no_grad():
+        m.fc1.weight.add_(1.0)                      # bumps the version counter
+    assert m._weights_fingerprint() != f0
+    m.invalidate_plans()
+    assert m._plans == {}
+
+
+def test_training_forward_delegates_to_a_reference_object():
+    """forward(sequences, output) is outside the accelerated path: with a delegate attached it runs there on this model's weights."""
+    import torch
+    import moleculediffusiontransformer_b200 as mdt
+
+    torch.manual_seed(0)
+    kw = dict(max_length=64, pred_dim=16, channels=64, unet_type="cfg", context_embedding_max_length=12,
+              pos_emb_fourier=True, pos_emb_fourier_add=False, text_embed_dim=64, embed_dim_position=64)
+    m = mdt.QMDiffusion(**kw)
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(2, 12), torch.zeros(2, 16, 64))
+
+    class FakeReference(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.loaded = None
+        def load_state_dict(self, sd, *a, **k):
+            self.loaded = {k2: v.clone() for k2, v in sd.items()}
+        def forward(self, sequences, output):
+            return output.mean() + self.loaded["fc1.bias"].sum() * 0
+
+    ref = FakeReference()
+    m.set_training_delegate(ref)
+    loss = m(torch.zeros(2, 12), torch.ones(2, 16, 64))
+    assert float(loss) == 1.0 and set(ref.loaded) == set(m.state_dict())

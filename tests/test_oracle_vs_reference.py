@@ -39,3 +39,22 @@ def test_state_dict_layout_and_init_live():
     assert b[k].data_ptr() == b["diffusion.net." + k[5:]].data_ptr() == b["diffusion.diffusion.net." + k[5:]].data_ptr()
     ref.load_state_dict(b, strict=True)
     mine.load_state_dict(a, strict=True)
+
+
+def test_training_forward_delegate_live():
+    """set_training_delegate: the reference object computes the training loss (generative.py:812-833) on this model's weights."""
+    import moleculediffusiontransformer_b200 as mdt
+    kind, kw, mseed, *_ = CASES["inv64_cs1"]
+    torch.manual_seed(3)
+    mine = mdt.QMDiffusion(**kw)
+    ref = rl.build_model(kind, seed=7, **kw)                 # different weights: the delegate must take ours
+    mine.set_training_delegate(ref)
+    g = torch.Generator().manual_seed(1)
+    seq, out = torch.rand(2, 12, generator=g), torch.rand(2, 16, 64, generator=g) * 2 - 1
+    torch.manual_seed(11)
+    loss = mine(seq, out)
+    ref2 = rl.build_model(kind, seed=9, **kw)
+    ref2.load_state_dict(mine.state_dict(), strict=True)
+    torch.manual_seed(11)
+    want = ref2(seq, out)
+    assert loss.dim() == 0 and torch.equal(loss, want)
