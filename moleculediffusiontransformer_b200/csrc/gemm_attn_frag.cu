@@ -37,8 +37,22 @@ __device__ __forceinline__ void tmem_ld16x256_x4(uint32_t taddr, uint32_t (&r)[1
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void mma_f16_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// two fp32 values -> one f16x2 register (low half = first): fp16 carries the same 11-bit significand as tf32, so the attention core
+// keeps its precision while one m16n8k16 MMA replaces two m16n8k8 ones (operands here are O(1) after LayerNorm: no range issue)
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // softmax over <= 16 keys held as two m16n8 score tiles (thread: rows g / g + 8, keys 8t + 2q, 8t + 2q + 1); returns the
 // probabilities as tf32 A fragments of P V (key permutation of attn_math.cuh).  bm: block-diagonal mask (~(blk - 1)) or 0.
+template <bool F16>
 __device__ __forceinline__ void softmax_2tiles(float (&sc)[2][4], int nk, float scale, int bm, int g, int q, uint32_t (&pa)[2][4]) {
   float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
@@ -64,6 +78,14 @@ __device__ __forceinline__ void softmax_2tiles(float (&sc)[2][4], int nk, float 
   s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
   s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
   const float inv0 = 1.0f / s0, inv1 = 1.0f / s1;
+  if (F16) {
+    // one m16n8k16 A fragment over the 16 keys: a0 = (row g, keys 2q, 2q + 1), a1 = (row g + 8, same), a2 / a3 = keys + 8
+    pa[0][0] = pack_f16(sc[0][0] * inv0, sc[0][1] * inv0);
+    pa[0][1] = pack_f16(sc[0][2] * inv1, sc[0][3] * inv1);
+    pa[0][2] = pack_f16(sc[1][0] * inv0, sc[1][1] * inv0);
+    pa[0][3] = pack_f16(sc[1][2] * inv1, sc[1][3] * inv1);
+    return;
+  }
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     pa[t][0] = to_tf32(sc[t][0] * inv0);   // (row g,     key 8t + 2q)
@@ -108,7 +130,8 @@ __device__ __forceinline__ void store_o_tiles(const float (&oc)[8][4], void* out
 
 // MODE: 0 self (L in {4, 8, 16}: 16 rows = 16 / L samples, block-diagonal mask when L < 16);  4 / 8 / 16: cross-attention on the
 // fragment-ordered cache with that many query rows per sample (compile time: 16 / MODE samples share the m16 tile)
-template <int KIND, int MODE>
+// MATH: 0 = tf32 m16n8k8 attention core, 1 = f16 m16n8k16 (same 11-bit significand, half the MMAs and fragment loads)
+template <int KIND, int MODE, int MATH>
 __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmS,
@@ -119,6 +142,10 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
   constexpr bool CROSS = MODE != 0;
   constexpr int LQ = CROSS ? MODE : 16;
   constexpr int G = 16 / LQ;                // samples sharing one m16 tile (cross)
+  constexpr bool F16 = MATH == 1;
+  constexpr int NKF = F16 ? 8 : 16;         // K (and V) fragments per (sample, head) block of the cross-attention cache
+  constexpr int VOFF = F16 ? 256 : 512;     // uint2 offset of the V fragments inside a block
+  constexpr int VKP = 24;                   // f16 v tile: halfs per feature row (16 keys + 8 padding: conflict-free 32-bit fragment loads)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[Z_MAXST];
   __shared__ __align__(8) uint64_t empty_bar[Z_MAXST];
@@ -326,7 +353,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
         // cross: the K / V fragment blocks of this tile's samples and head; with one sample per tile the K fragments are fetched
         // before the accumulator wait (they do not depend on the projection), so their L2 / HBM latency hides behind it
         const uint2* kvp[G];
-        uint2 kb[16];
+        uint2 kb[NKF];
         if constexpr (CROSS) {
           const int bs = mrow / LQ;
 #pragma unroll
@@ -337,7 +364,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
           }
           if (G == 1 && rows_valid > 0) {
 #pragma unroll
-            for (int f = 0; f < 16; ++f) kb[f] = __ldg(kvp[0] + f * 32 + lane);
+            for (int f = 0; f < NKF; ++f) kb[f] = __ldg(kvp[0] + f * 32 + lane);
           }
         }
         mbar_wait(&acc_full[buf], (uint32_t)(j >> 1) & 1u);
@@ -361,10 +388,19 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const bool z0 = g >= rows_valid, z1 = g + 8 >= rows_valid;
-              *reinterpret_cast<uint2*>(vt + g * Z_VLD + hf * 32 + 8 * c + 2 * q) =
-                  make_uint2(z0 ? 0u : to_tf32(__uint_as_float(vf[4 * c])), z0 ? 0u : to_tf32(__uint_as_float(vf[4 * c + 1])));
-              *reinterpret_cast<uint2*>(vt + (g + 8) * Z_VLD + hf * 32 + 8 * c + 2 * q) =
-                  make_uint2(z1 ? 0u : to_tf32(__uint_as_float(vf[4 * c + 2])), z1 ? 0u : to_tf32(__uint_as_float(vf[4 * c + 3])));
+              if (F16) {
+                // transposed f16 tile [feature][key]: a B fragment of P V (two consecutive keys of one feature) is one 32-bit load
+                __half* vh = reinterpret_cast<__half*>(vt) + (hf * 32 + 8 * c + 2 * q) * VKP + g;
+                vh[0] = __float2half_rn(z0 ? 0.f : __uint_as_float(vf[4 * c]));
+                vh[VKP] = __float2half_rn(z0 ? 0.f : __uint_as_float(vf[4 * c + 1]));
+                vh[8] = __float2half_rn(z1 ? 0.f : __uint_as_float(vf[4 * c + 2]));
+                vh[VKP + 8] = __float2half_rn(z1 ? 0.f : __uint_as_float(vf[4 * c + 3]));
+              } else {
+                *reinterpret_cast<uint2*>(vt + g * Z_VLD + hf * 32 + 8 * c + 2 * q) =
+                    make_uint2(z0 ? 0u : to_tf32(__uint_as_float(vf[4 * c])), z0 ? 0u : to_tf32(__uint_as_float(vf[4 * c + 1])));
+                *reinterpret_cast<uint2*>(vt + (g + 8) * Z_VLD + hf * 32 + 8 * c + 2 * q) =
+                    make_uint2(z1 ? 0u : to_tf32(__uint_as_float(vf[4 * c + 2])), z1 ? 0u : to_tf32(__uint_as_float(vf[4 * c + 3])));
+              }
             }
           }
           // ---- scores: q and k fragments straight from TMEM, 32 features per pass
@@ -375,11 +411,21 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
             tmem_ld16x256_x4(tq + (uint32_t)(d + hf * 32), kf);
             tmem_ld_wait();
             add_q_bias<KIND>(qf, a.bias + h * d + hf * 32, q);
+            if (F16) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t af[4] = {qf[4 * c], qf[4 * c + 2], qf[4 * c + 1], qf[4 * c + 3]};
-              mma_tf32_16x8x8(sc[0], af, kf[4 * c], kf[4 * c + 1]);          // keys g
-              mma_tf32_16x8x8(sc[1], af, kf[4 * c + 2], kf[4 * c + 3]);      // keys g + 8
+              for (int c = 0; c < 4; c += 2) {     // one k16 step = two 8-column quads
+                auto pk = [](const uint32_t (&r)[16], int i) { return pack_f16(__uint_as_float(r[i]), __uint_as_float(r[i + 1])); };
+                const uint32_t af[4] = {pk(qf, 4 * c), pk(qf, 4 * c + 2), pk(qf, 4 * c + 4), pk(qf, 4 * c + 6)};
+                mma_f16_16x8x16(sc[0], af, pk(kf, 4 * c), pk(kf, 4 * c + 4));          // keys g
+                mma_f16_16x8x16(sc[1], af, pk(kf, 4 * c + 2), pk(kf, 4 * c + 6));      // keys g + 8
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t af[4] = {qf[4 * c], qf[4 * c + 2], qf[4 * c + 1], qf[4 * c + 3]};
+                mma_tf32_16x8x8(sc[0], af, kf[4 * c], kf[4 * c + 1]);          // keys g
+                mma_tf32_16x8x8(sc[1], af, kf[4 * c + 2], kf[4 * c + 3]);      // keys g + 8
+              }
             }
           }
           tc_fence_before();
@@ -387,13 +433,19 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
           if (lane == 0) mbar_arrive(&acc_empty[buf]);       // every TMEM read of this warp is complete
           if (rows_valid > 0) {
             uint32_t pa[2][4];
-            softmax_2tiles(sc, 16, a.scale, bm, g, q, pa);
+            softmax_2tiles<F16>(sc, 16, a.scale, bm, g, q, pa);
+            if (F16) {
+              const uint32_t* v0 = reinterpret_cast<const uint32_t*>(vt) + g * (VKP / 2) + q;     // feature 8n + g, keys 2q, 2q + 1
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const float* v0 = vt + (t * 8 + 2 * q) * Z_VLD + g;
+              for (int n = 0; n < 8; ++n) mma_f16_16x8x16(oc[n], pa[0], v0[n * 8 * (VKP / 2)], v0[n * 8 * (VKP / 2) + 4]);
+            } else {
 #pragma unroll
-              for (int n = 0; n < 8; ++n)
-                mma_tf32_16x8x8(oc[n], pa[t], __float_as_uint(v0[n * 8]), __float_as_uint(v0[Z_VLD + n * 8]));
+              for (int t = 0; t < 2; ++t) {
+                const float* v0 = vt + (t * 8 + 2 * q) * Z_VLD + g;
+#pragma unroll
+                for (int n = 0; n < 8; ++n)
+                  mma_tf32_16x8x8(oc[n], pa[t], __float_as_uint(v0[n * 8]), __float_as_uint(v0[Z_VLD + n * 8]));
+              }
             }
             store_o_tiles<KIND>(oc, obuf, ob, ldo, rows_valid, g, q, fused ? l2pol : 0);
           }
@@ -415,23 +467,39 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
             for (int t = 0; t < G; ++t)
 #pragma unroll
               for (int nt = 0; nt < 2; ++nt) { st[t][nt][0] = 0.f; st[t][nt][1] = 0.f; st[t][nt][2] = 0.f; st[t][nt][3] = 0.f; }
+            if (F16) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              const int c = ks & 3;
-              const uint32_t af[4] = {qf[ks >> 2][4 * c], qf[ks >> 2][4 * c + 2], qf[ks >> 2][4 * c + 1], qf[ks >> 2][4 * c + 3]};
+              for (int ks = 0; ks < 4; ++ks) {     // k16 steps
+                const int c = 2 * (ks & 1);
+                auto pk = [](const uint32_t (&r)[16], int i) { return pack_f16(__uint_as_float(r[i]), __uint_as_float(r[i + 1])); };
+                const uint32_t af[4] = {pk(qf[ks >> 1], 4 * c), pk(qf[ks >> 1], 4 * c + 2), pk(qf[ks >> 1], 4 * c + 4), pk(qf[ks >> 1], 4 * c + 6)};
 #pragma unroll
-              for (int t = 0; t < G; ++t)
+                for (int t = 0; t < G; ++t)
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                  const uint2 bb = (G == 1) ? kb[ks * 2 + nt] : __ldg(kvp[t] + (ks * 2 + nt) * 32 + lane);
-                  mma_tf32_16x8x8(st[t][nt], af, bb.x, bb.y);
-                }
+                  for (int nt = 0; nt < 2; ++nt) {
+                    const uint2 bb = (G == 1) ? kb[ks * 2 + nt] : __ldg(kvp[t] + (ks * 2 + nt) * 32 + lane);
+                    mma_f16_16x8x16(st[t][nt], af, bb.x, bb.y);
+                  }
+              }
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                const int c = ks & 3;
+                const uint32_t af[4] = {qf[ks >> 2][4 * c], qf[ks >> 2][4 * c + 2], qf[ks >> 2][4 * c + 1], qf[ks >> 2][4 * c + 3]};
+#pragma unroll
+                for (int t = 0; t < G; ++t)
+#pragma unroll
+                  for (int nt = 0; nt < 2; ++nt) {
+                    const uint2 bb = (G == 1) ? kb[(ks * 2 + nt) % NKF] : __ldg(kvp[t] + (ks * 2 + nt) * 32 + lane);
+                    mma_tf32_16x8x8(st[t][nt], af, bb.x, bb.y);
+                  }
+              }
             }
             // one sample per tile: fetch the V fragments now, their latency hides behind the softmax
-            uint2 vb[16];
+            uint2 vb[NKF];
             if (G == 1) {
 #pragma unroll
-              for (int f = 0; f < 16; ++f) vb[f] = __ldg(kvp[0] + 512 + f * 32 + lane);
+              for (int f = 0; f < NKF; ++f) vb[f] = __ldg(kvp[0] + VOFF + f * 32 + lane);
             }
             // row g belongs to sample t0 = g / LQ, row g + 8 to sample t1 = (g + 8) / LQ: pick their score blocks
             const int t0 = g / LQ, t1 = (g + 8) / LQ;
@@ -446,17 +514,26 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
               sc[nt][0] = a0; sc[nt][1] = a1; sc[nt][2] = b0; sc[nt][3] = b1;
             }
             uint32_t pa[2][4];
-            softmax_2tiles(sc, a.nk, a.scale, 0, g, q, pa);
+            softmax_2tiles<F16>(sc, a.nk, a.scale, 0, g, q, pa);
 #pragma unroll
             for (int t = 0; t < G; ++t) {
               const bool own0 = t0 == t, own1 = t1 == t;
-#pragma unroll
-              for (int kt = 0; kt < 2; ++kt) {
-                const uint32_t af[4] = {own0 ? pa[kt][0] : 0u, own1 ? pa[kt][1] : 0u, own0 ? pa[kt][2] : 0u, own1 ? pa[kt][3] : 0u};
+              if (F16) {
+                const uint32_t af[4] = {own0 ? pa[0][0] : 0u, own1 ? pa[0][1] : 0u, own0 ? pa[0][2] : 0u, own1 ? pa[0][3] : 0u};
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
-                  const uint2 bb = (G == 1) ? vb[kt * 8 + n] : __ldg(kvp[t] + 512 + (kt * 8 + n) * 32 + lane);
-                  mma_tf32_16x8x8(oc[n], af, bb.x, bb.y);
+                  const uint2 bb = (G == 1) ? vb[n] : __ldg(kvp[t] + VOFF + n * 32 + lane);
+                  mma_f16_16x8x16(oc[n], af, bb.x, bb.y);
+                }
+              } else {
+#pragma unroll
+                for (int kt = 0; kt < 2; ++kt) {
+                  const uint32_t af[4] = {own0 ? pa[kt][0] : 0u, own1 ? pa[kt][1] : 0u, own0 ? pa[kt][2] : 0u, own1 ? pa[kt][3] : 0u};
+#pragma unroll
+                  for (int n = 0; n < 8; ++n) {
+                    const uint2 bb = (G == 1) ? vb[(kt * 8 + n) % NKF] : __ldg(kvp[t] + VOFF + (kt * 8 + n) * 32 + lane);
+                    mma_tf32_16x8x8(oc[n], af, bb.x, bb.y);
+                  }
                 }
               }
             }
@@ -512,19 +589,22 @@ bool attn_frag_supported(int kind, int C, int L, int heads, int d, int cross, in
 typedef void (*AttnFragKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnLayerParams,
                                const uint32_t, const uint32_t);
 // mode: 0 self; 4 / 8 / 16 cross with that many query rows per sample
-static AttnFragKernel attn_frag_variant(int kind, int mode) {
-  static const AttnFragKernel tab[2][4] = {
-      {tc::attn_frag_kernel<1, 0>, tc::attn_frag_kernel<1, 4>, tc::attn_frag_kernel<1, 8>, tc::attn_frag_kernel<1, 16>},
-      {tc::attn_frag_kernel<2, 0>, tc::attn_frag_kernel<2, 4>, tc::attn_frag_kernel<2, 8>, tc::attn_frag_kernel<2, 16>}};
-  return tab[kind == 1 ? 0 : 1][mode == 0 ? 0 : (mode == 4 ? 1 : (mode == 8 ? 2 : 3))];
+static AttnFragKernel attn_frag_variant(int kind, int mode, int f16) {
+  static const AttnFragKernel tab[2][2][4] = {
+      {{tc::attn_frag_kernel<1, 0, 0>, tc::attn_frag_kernel<1, 4, 0>, tc::attn_frag_kernel<1, 8, 0>, tc::attn_frag_kernel<1, 16, 0>},
+       {tc::attn_frag_kernel<1, 0, 1>, tc::attn_frag_kernel<1, 4, 1>, tc::attn_frag_kernel<1, 8, 1>, tc::attn_frag_kernel<1, 16, 1>}},
+      {{tc::attn_frag_kernel<2, 0, 0>, tc::attn_frag_kernel<2, 4, 0>, tc::attn_frag_kernel<2, 8, 0>, tc::attn_frag_kernel<2, 16, 0>},
+       {tc::attn_frag_kernel<2, 0, 1>, tc::attn_frag_kernel<2, 4, 1>, tc::attn_frag_kernel<2, 8, 1>, tc::attn_frag_kernel<2, 16, 1>}}};
+  return tab[kind == 1 ? 0 : 1][f16 ? 1 : 0][mode == 0 ? 0 : (mode == 4 ? 1 : (mode == 8 ? 2 : 3))];
 }
 
 cudaError_t init_attn_frag() {
   for (int kind = 1; kind <= 2; ++kind)
-    for (int mode : {0, 4, 8, 16}) {
-      cudaError_t e = cudaFuncSetAttribute(attn_frag_variant(kind, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Z_SMEM_LIMIT);
-      if (e != cudaSuccess) return e;
-    }
+    for (int mode : {0, 4, 8, 16})
+      for (int f16 = 0; f16 < 2; ++f16) {
+        cudaError_t e = cudaFuncSetAttribute(attn_frag_variant(kind, mode, f16), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Z_SMEM_LIMIT);
+        if (e != cudaSuccess) return e;
+      }
   return cudaSuccess;
 }
 
@@ -546,7 +626,7 @@ cudaError_t launch_attn_frag(const void* tmA, const void* tmB, const void* tmS, 
   const int nitems = ((a.M + tc::Z_TM - 1) / tc::Z_TM) * (p.fused ? 1 : a.heads);
   const int sms = attn_layer_sms();
   const unsigned grid = (unsigned)(nitems < sms ? nitems : sms);
-  attn_frag_variant(kind, a.cross ? a.L : 0)<<<grid, tc::Z_THREADS, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(tmA),
+  attn_frag_variant(kind, a.cross ? a.L : 0, p.f16)<<<grid, tc::Z_THREADS, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(tmA),
                                                                      *reinterpret_cast<const CUtensorMap*>(tmB),
                                                                      *reinterpret_cast<const CUtensorMap*>(tmS),
                                                                      *reinterpret_cast<const CUtensorMap*>(tmW), p, idesc, idesc_o);

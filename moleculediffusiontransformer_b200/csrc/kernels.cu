@@ -929,6 +929,28 @@ __global__ void kv_fragment_pack_kernel(const float* __restrict__ kv, uint2* __r
   if (b >= B) return;
   const int ldkv = 2 * heads * d;
   const float* base = kv + (size_t)b * nk * ldkv + (size_t)h * d;
+  if (kperm == 2) {
+    // f16 m16n8k16 B fragments: K: f = kstep16 * 2 + ntile, b0 = (K[8 ntile + g][16 ks + 2q], [.. + 1]), b1 = the pair 8 features on;
+    // V: f = feature tile n, b0 = (V[2q][8n + g], V[2q + 1][8n + g]), b1 = the pair of keys 8 on.  512 uint2 per block.
+    const float* v = base + heads * d;
+    for (int idx = threadIdx.x; idx < 512; idx += blockDim.x) {
+      const int which = idx >> 8, f = (idx >> 5) & 7, lane = idx & 31, g = lane >> 2, q = lane & 3;
+      float e[4] = {0.f, 0.f, 0.f, 0.f};
+      if (which == 0) {
+        const int key = (f & 1) * 8 + g, c0 = (f >> 1) * 16 + 2 * q;
+        if (key < nk) { e[0] = base[(size_t)key * ldkv + c0]; e[1] = base[(size_t)key * ldkv + c0 + 1]; e[2] = base[(size_t)key * ldkv + c0 + 8]; e[3] = base[(size_t)key * ldkv + c0 + 9]; }
+      } else {
+        const int col = f * 8 + g;
+        const int ks[4] = {2 * q, 2 * q + 1, 2 * q + 8, 2 * q + 9};
+        for (int i = 0; i < 4; ++i) if (ks[i] < nk) e[i] = v[(size_t)ks[i] * ldkv + col];
+      }
+      uint32_t r0, r1;
+      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r0) : "f"(e[1]), "f"(e[0]));
+      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r1) : "f"(e[3]), "f"(e[2]));
+      out[(size_t)bh * 1024 + idx] = make_uint2(r0, r1);
+    }
+    return;
+  }
   for (int idx = threadIdx.x; idx < 1024; idx += blockDim.x) {
     const int which = idx >> 9, f = (idx >> 5) & 15, lane = idx & 31, g = lane >> 2, q = lane & 3;
     float b0 = 0.f, b1 = 0.f;

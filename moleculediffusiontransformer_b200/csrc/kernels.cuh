@@ -154,7 +154,8 @@ cudaError_t launch_inpaint(int mode, float* x, float* xin, const float* source, 
                            float sigma, float c_in, unsigned long long seed, unsigned long long sample_offset, int stream, int B,
                            int P, int L, int cfg, float* out, cudaStream_t s);
 cudaError_t launch_set_run_params(RunParams* dst, const RunParams& v, cudaStream_t s);
-// kperm != 0: K fragments in the permuted k order of gemm_attn_frag.cu (b0 = K[key][8 ks + 2q], b1 = K[key][8 ks + 2q + 1])
+// kperm = 1: K fragments in the permuted k order of gemm_attn_frag.cu (b0 = K[key][8 ks + 2q], b1 = K[key][8 ks + 2q + 1]);
+// kperm = 2: f16 m16n8k16 fragments (8 K + 8 V fragments of f16x2 pairs per block, half the bytes)
 cudaError_t launch_kv_fragment_pack(const float* kv, void* out, long long B, int nk, int heads, int d, int kperm, cudaStream_t s);
 cudaError_t launch_decode_tokens(const uint8_t* tokens, const uint8_t* lut, uint8_t* out, int* lengths, long long B, int L, cudaStream_t s);
 cudaError_t launch_set_int(int* dst, int v, cudaStream_t s);
@@ -239,6 +240,7 @@ struct AttnLayerParams {
   float* C32; int ldc;     // fp32 output
   void* Cop; int ldcop;    // operand-dtype copy of the output (the next GEMM's A operand) or null
   void* scratch;           // [SMs][attn_layer_slots(heads)][128][d] operand dtype: CTA-private head-output slots (L2 resident)
+  int f16;                 // gemm_attn_frag.cu: attention core on f16 m16n8k16 MMAs (cross: K / V cache packed with kperm = 2)
   int l2_hint;             // scratch stores carry an L2 evict_last policy (MDT_L2_HINT=1; measured in profiles/README.md)
   int fused;               // 1: out-projection inside the kernel; 0 (gemm_attn_frag.cu only): head outputs go to a.att, one work item per (row block, head)
   int nslot;               // filled by the launcher from here on

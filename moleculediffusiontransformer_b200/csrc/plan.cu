@@ -437,7 +437,8 @@ struct Builder {
       memset(op.tmC, 0, sizeof op.tmC); memset(op.tmD, 0, sizeof op.tmD);
     }
     op.frag = fused ? frag_ok(C, L, cross) : true;
-    if (cross && cross_layer >= 0) pl.cross[cross_layer].kperm = op.frag ? 1 : 0;
+    { const char* hf = getenv("MDT_ATTN_F16"); y.f16 = (op.frag && !(hf && hf[0] == '0')) ? 1 : 0; }
+    if (cross && cross_layer >= 0) pl.cross[cross_layer].kperm = op.frag ? (y.f16 ? 2 : 1) : 0;
     emit(prog, op);
   }
 
