@@ -27,12 +27,14 @@ constexpr int T_STAGE_BYTES = T_A_BYTES + T_B_BYTES;
 constexpr int T_EPI_WARPS = 16;
 constexpr int T_STG_LD = 36;                                  // 32 columns + 4 floats of padding per staged row
 constexpr int T_STG_BYTES = T_EPI_WARPS * 32 * T_STG_LD * 4;  // per-warp private staging, 4.5 KB each
-constexpr int T_SMEM_BYTES = T_STAGES * T_STAGE_BYTES + T_STG_BYTES + 1024;
+// LayerNorm epilogue (cop_ln): per-row (mean, M2) of each of the four column-group warps, double buffered by tile parity
+constexpr int T_XCH_BYTES = 2 * T_TM * 4 * 8;
+constexpr int T_SMEM_BYTES = T_STAGES * T_STAGE_BYTES + T_STG_BYTES + T_XCH_BYTES + 1024;
 // BN = 256 (one n-tile for the 256-wide levels: the activation tile is streamed once per row block instead of twice, -25 % L2 -> SM
 // operand bytes): 48 KB stages, three of them
 constexpr int T_STAGES_WIDE = 3;
 constexpr int T_STAGE_BYTES_WIDE = T_A_BYTES + 256 * 128;
-constexpr int T_SMEM_BYTES_WIDE = T_STAGES_WIDE * T_STAGE_BYTES_WIDE + T_STG_BYTES + 1024;
+constexpr int T_SMEM_BYTES_WIDE = T_STAGES_WIDE * T_STAGE_BYTES_WIDE + T_STG_BYTES + T_XCH_BYTES + 1024;
 constexpr int T_THREADS = 64 + 32 * T_EPI_WARPS;
 
 // Persistent kernel: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... with the N tile index
@@ -40,7 +42,8 @@ constexpr int T_THREADS = 64 + 32 * T_EPI_WARPS;
 //   smem ring  (TMA producer  <-> MMA issuer)        full_bar / empty_bar       [T_STAGES]
 //   TMEM ring  (MMA issuer    <-> epilogue warps)    acc_full / acc_empty       [2 accumulators of BN columns]
 //   tile loop  (all roles derive the same tile sequence from blockIdx / gridDim)
-template <int KIND>
+// LN: the LayerNorm epilogue variant (its own instantiation: the register copy of the row block must not cost the plain GEMMs anything)
+template <int KIND, bool LN>
 __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const TmaGemmParams p, const uint32_t idesc) {
@@ -137,12 +140,108 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
     const int ngroups = BN >= 128 ? 4 : (BN >= 64 ? 2 : 1);
     const int cols_per_half = BN / ngroups;
     const bool active = half < ngroups;
+    float2* xch = reinterpret_cast<float2*>(smem + NST * stage_bytes + T_STG_BYTES);       // [2][128 rows][4 column groups]
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int te = p.rev ? total_tiles - 1 - t : t;
       const int mt = te / n_tiles, nt = te - mt * n_tiles;
       const int buf = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      if (LN) {
+        // ---- LayerNorm epilogue (launcher guarantees N == BN in {128, 256}: a row block holds whole rows, four warps per quadrant
+        // own 32 or 64 columns each).  C32 = acc + bias (+ res); Cop = (C32 - mean) * rstd, no affine (folded into the consumer's
+        // weights).  Two-pass statistics on the register copy: exact mean / centred M2 per 32-column chunk inside the eight lanes
+        // that hold it, equal-count Chan merges across chunks and across the four warps (one named barrier per tile).
+        const int nch = cols_per_half >> 5;          // 1 or 2 chunks of 32 columns per warp
+        const int cl = (lane & 7) * 4, r0 = lane >> 3;
+        const int m0 = mt * T_TM + q * 32;
+        float4 r[2][8];
+        auto load_res = [&](int u) {
+          const int no = half * cols_per_half + u * 32 + cl;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int mo = m0 + r0 + i * 4;
+            r[u][i] = (p.res && mo < p.M) ? *reinterpret_cast<const float4*>(p.res + (size_t)mo * p.ldres + no) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        load_res(0);                                 // ahead of the accumulator wait: the residual's latency hides behind it
+        mbar_wait(&acc_full[buf], aphase);
+        tc_fence_after();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u < nch) {
+            const int col0 = half * cols_per_half + u * 32;
+            {
+              uint32_t v[32];
+              tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0), v);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(stg + lane * T_STG_LD + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            __syncwarp();
+            if (u > 0) load_res(u);      // after the staging registers are dead (register budget: 576 threads)
+            const int no = col0 + cl;
+            const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + no)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int mo = m0 + r0 + i * 4;
+              float4 o = *reinterpret_cast<const float4*>(stg + (r0 + i * 4) * T_STG_LD + cl);
+              o.x += bv.x + r[u][i].x; o.y += bv.y + r[u][i].y; o.z += bv.z + r[u][i].z; o.w += bv.w + r[u][i].w;
+              r[u][i] = o;
+              if (p.C32 && mo < p.M) *reinterpret_cast<float4*>(p.C32 + (size_t)mo * p.ldc + no) = o;
+            }
+            __syncwarp();
+          }
+        }
+        // the accumulator lives in registers now: hand it back before the statistics exchange
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        float2* xb = xch + (size_t)(it & 1) * T_TM * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float mean_w = 0.f, m2_w = 0.f, mean0 = 0.f;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (u < nch) {
+              const float4 o = r[u][i];
+              float sm = (o.x + o.y) + (o.z + o.w);
+              sm += __shfl_xor_sync(0xffffffffu, sm, 1); sm += __shfl_xor_sync(0xffffffffu, sm, 2); sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+              const float mean = sm * (1.0f / 32.0f);
+              const float dx = o.x - mean, dy = o.y - mean, dz = o.z - mean, dw = o.w - mean;
+              float m2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+              m2 += __shfl_xor_sync(0xffffffffu, m2, 1); m2 += __shfl_xor_sync(0xffffffffu, m2, 2); m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
+              if (u == 0) { mean_w = mean; m2_w = m2; mean0 = mean; }
+              else { const float dm = mean - mean0; mean_w = 0.5f * (mean0 + mean); m2_w = m2_w + m2 + 16.0f * dm * dm; }
+            }
+          }
+          if ((lane & 7) == 0) xb[(q * 32 + r0 + i * 4) * 4 + half] = make_float2(mean_w, m2_w);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");      // the four column-group warps of this quadrant
+        const float inv_n = 1.0f / (float)p.N, n_w = (float)cols_per_half;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 e01 = *reinterpret_cast<const float4*>(xb + (q * 32 + r0 + i * 4) * 4);
+          const float4 e23 = *reinterpret_cast<const float4*>(xb + (q * 32 + r0 + i * 4) * 4 + 2);
+          const float mean = 0.25f * ((e01.x + e01.z) + (e23.x + e23.z));
+          const float d0 = e01.x - mean, d1 = e01.z - mean, d2 = e23.x - mean, d3 = e23.z - mean;
+          const float dev = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+          const float rstd = rsqrtf(fmaf(n_w, dev, (e01.y + e01.w) + (e23.y + e23.w)) * inv_n + p.ln_eps);
+          const int mo = m0 + r0 + i * 4;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (u < nch && mo < p.M) {
+              const float4 o = r[u][i];
+              const float nx = (o.x - mean) * rstd, ny = (o.y - mean) * rstd, nz = (o.z - mean) * rstd, nw = (o.w - mean) * rstd;
+              const size_t off = (size_t)mo * p.ldcop + half * cols_per_half + u * 32 + cl;
+              if (KIND == 1) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.Cop) + off) = make_uint4(to_tf32(nx), to_tf32(ny), to_tf32(nz), to_tf32(nw));
+              else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.Cop) + off) = make_uint2(pack_bf16(nx, ny), pack_bf16(nz, nw));
+            }
+          }
+        }
+        // no second barrier: the next tile uses the other exchange buffer, and that tile's barrier orders the reuse of this one
+        continue;
+      }
       mbar_wait(&acc_full[buf], aphase);
       tc_fence_after();
       if (active) {
@@ -328,9 +427,11 @@ int make_tmap_weight(void* map128, const void* base, int kind, long long K, int 
 
 cudaError_t init_gemm_tma() {
   const int mx = tc::T_SMEM_BYTES_WIDE > tc::T_SMEM_BYTES ? tc::T_SMEM_BYTES_WIDE : tc::T_SMEM_BYTES;
-  cudaError_t e = cudaFuncSetAttribute(tc::gemm_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(tc::gemm_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaError_t e = cudaFuncSetAttribute(tc::gemm_tma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  return e;
 }
 
 static int g_num_sms = 0;
@@ -338,6 +439,7 @@ static int g_num_sms = 0;
 cudaError_t launch_gemm_tma(const void* tmA, const void* tmB, const TmaGemmParams& p, int kind, cudaStream_t s) {
   if (p.M <= 0 || p.N <= 0) return cudaSuccess;
   if (p.BN <= 0 || p.N % p.BN) return cudaErrorInvalidValue;
+  if (p.cop_ln && (p.N != p.BN || p.BN < 128 || !p.Cop || p.gn_L > 0 || p.act != 0)) return cudaErrorInvalidValue;
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -351,8 +453,11 @@ cudaError_t launch_gemm_tma(const void* tmA, const void* tmB, const TmaGemmParam
   const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(tmA);
   const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(tmB);
   const int smem = p.BN > 128 ? tc::T_SMEM_BYTES_WIDE : tc::T_SMEM_BYTES;
-  if (kind == 1) tc::gemm_tma_kernel<1><<<grid, tc::T_THREADS, smem, s>>>(a, b, p, idesc);
-  else tc::gemm_tma_kernel<2><<<grid, tc::T_THREADS, smem, s>>>(a, b, p, idesc);
+  if (p.cop_ln) {
+    if (kind == 1) tc::gemm_tma_kernel<1, true><<<grid, tc::T_THREADS, smem, s>>>(a, b, p, idesc);
+    else tc::gemm_tma_kernel<2, true><<<grid, tc::T_THREADS, smem, s>>>(a, b, p, idesc);
+  } else if (kind == 1) tc::gemm_tma_kernel<1, false><<<grid, tc::T_THREADS, smem, s>>>(a, b, p, idesc);
+  else tc::gemm_tma_kernel<2, false><<<grid, tc::T_THREADS, smem, s>>>(a, b, p, idesc);
   return cudaGetLastError();
 }
 

@@ -197,6 +197,7 @@ struct TmaGemmParams {
   int gn_L, gn_cpg; float gn_eps;
   const float* gn_aff; int gn_aff_stride; const int* gn_call;
   int rev;                    // walk the row tiles from the end (serpentine order: start with what the producer wrote last)
+  int cop_ln; float ln_eps;   // Cop = LayerNorm(C32 row) without affine (N == BN: the row block holds whole rows) instead of the raw copy
 };
 // 128-byte CUtensorMap blobs (64-byte aligned) built on the host
 int make_tmap_act(void* map128, const void* base, int kind, int C, int L, long long samples);

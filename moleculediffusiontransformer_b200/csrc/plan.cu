@@ -327,17 +327,24 @@ struct Builder {
   }
   // A: operand-dtype activation [Beff_max * L][C]; dW32: packed fp32 weights [N][taps * C] already on the device
   void emit_gemm_tma(std::vector<Op>& prog, const void* A, int C, int L, int taps, const float* dW32, const float* bias, int N,
-                     int act, const float* res, float* C32, void* Cop, int ldcop = 0) {
+                     int act, const float* res, float* C32, void* Cop, int ldcop = 0, bool cop_ln = false) {
     Op op; op.type = OP_GEMM_TMA; op.rps = L;
     const int kch = pl.prec == MDT_PREC_TF32 ? 32 : 64;
     TmaGemmParams& g = op.tg;
     g.M = 0; g.N = N; g.BN = tma_pick_bn(N); g.taps = taps; g.pad = taps / 2; g.kchunks = C / kch; g.C = C;
     g.L = L; g.Lb = L >= 128 ? 128 : L; g.Sb = L >= 128 ? 1 : 128 / L;
     g.bias = bias; g.act = act; g.res = res; g.ldres = N; g.C32 = C32; g.ldc = N; g.Cop = Cop; g.ldcop = ldcop ? ldcop : N;
+    g.cop_ln = cop_ln ? 1 : 0; g.ln_eps = 1e-5f;
     const void* wop = tc_copy(dW32, (size_t)N * taps * C);
     if (make_tmap_act(op.tmA, A, pl.prec, C, L, (long long)pl.Beff_max) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(activation C=%d L=%d) failed", C, L);
     if (make_tmap_weight(op.tmB, wop, pl.prec, (long long)taps * C, N, g.BN) != 0) raise(MDT_ERR_CUDA, "cuTensorMapEncodeTiled(weight K=%d N=%d) failed", taps * C, N);
     emit(prog, op);
+  }
+
+  // LayerNorm in the epilogue of the GEMM that produces the row (gemm_tma.cu cop_ln): the row block must hold whole rows
+  bool ln_epilogue_ok(int N) const {
+    static const bool off = getenv("MDT_NO_LN_EPILOGUE") != nullptr;
+    return !off && N >= 128 && tma_pick_bn(N) == N;
   }
 
   // FeedForward chain (gemm_chain.cu): t = t + b2 + GELU(x_op W0^T + b0) W2^T; the hidden activation goes through CTA-private
@@ -605,9 +612,12 @@ struct Builder {
     Src xs{x, C, nullptr, 0, 1.f};
     float* t = acquire();
     float* tn = fast ? acquire() : nullptr;   // normalised / raw operand copies of the token stream
+    bool to_in_ln = false;
     if (fast) {
       emit_gn_apply(prog, xs, L, 32, 1e-6f, nullptr, 0, nullptr, 0, tn, nullptr);
-      emit_gemm_tma(prog, tn, C, L, 1, d_wi, d_bi, C, 0, nullptr, t, nullptr);
+      // block 0's self-attention reads LayerNorm(t): written by this GEMM's epilogue where a row block holds whole rows
+      to_in_ln = ln_epilogue_ok(C) && has(pre + "blocks.0.attention.to_q.weight");
+      emit_gemm_tma(prog, tn, C, L, 1, d_wi, d_bi, C, 0, nullptr, t, to_in_ln ? (void*)tn : nullptr, 0, to_in_ln);
     } else {
       gn_stats(prog, xs, L, 32, 1e-6f);
       ALoad a = make_aload(xs, L, L, 1, 1, 0);
@@ -617,7 +627,8 @@ struct Builder {
     Src ts{t, C, nullptr, 0, 1.f};
     int nblocks = 0;
     while (has(pre + "blocks." + std::to_string(nblocks) + ".attention.to_q.weight")) ++nblocks;
-    bool tn_is_ln = false;   // tn already holds LayerNorm(t) (written by the previous block's FeedForward chain)
+    bool tn_is_ln = to_in_ln;   // tn already holds LayerNorm(t) (written by the epilogue that produced t)
+    bool cross_ln_done = false; // same, for the cross-attention stage of the current block
     for (int i = 0; i < nblocks; ++i) {
       const std::string bp = pre + "blocks." + std::to_string(i) + ".";
       const bool has_cross = has(bp + "cross_attention.to_q.weight");
@@ -635,6 +646,7 @@ struct Builder {
         }
         const float* d_w = upload(w); const float* d_b = upload(b);
         const bool fuse_self = fast && fuse_attn && gemm_attn_supported(pl.prec, C, L, heads, d, 0, 0);
+        cross_ln_done = false;
         const float* d_wr_self = nullptr; const float* d_bq_self = nullptr; bool layer_self = false;
         if (fuse_self) {
           // head-major repack: rows [h][q(64) | k(64) | v(64)]
@@ -689,8 +701,10 @@ struct Builder {
           emit_attn_layer(prog, tn, C, L, d_wr_self, d_bq_self, 0, -1, nullptr, nullptr, nullptr, d_wo, d_bo, t,
                           has_cross ? nullptr : (void*)tn);
         } else if (fast) {
-          // without a cross-attention stage the raw operand copy of the new token stream feeds FF1 directly
-          emit_gemm_tma(prog, pl.att, Hd, L, 1, d_wo, d_bo, C, 0, t, t, has_cross ? nullptr : (void*)tn);
+          // without a cross-attention stage the raw operand copy of the new token stream feeds FF1 directly; with one, the epilogue
+          // writes LayerNorm(t) for its q projection (not at the end of the CFG prefix: the null-branch rows are replicated there)
+          cross_ln_done = has_cross && !prefix && ln_epilogue_ok(C);
+          emit_gemm_tma(prog, pl.att, Hd, L, 1, d_wo, d_bo, C, 0, t, t, (!has_cross || cross_ln_done) ? (void*)tn : nullptr, 0, cross_ln_done);
         } else {
           Src as{pl.att, Hd, nullptr, 0, 1.f};
           emit(prog, gemm_op(make_aload(as, L, L, 1, 1, 0), d_wo, tc_copy(d_wo, (size_t)C * Hd), d_bo, C, 0, t, t, L));
@@ -729,19 +743,19 @@ struct Builder {
         pl.cross.push_back(cl);
         const bool layer_cross = fuse_cross && layer_ok(C, L, 1, packed);
         if (layer_cross) {
-          emit_ln_apply(prog, t, C, L, tn);
+          if (!cross_ln_done) emit_ln_apply(prog, t, C, L, tn);
         } else if (fuse_cross && packed && frag_ok(C, L, 1, false)) {
-          emit_ln_apply(prog, t, C, L, tn);
+          if (!cross_ln_done) emit_ln_apply(prog, t, C, L, tn);
           emit_attn_layer(prog, tn, C, L, d_wq, d_bq, 1, layer, cl.kv_null, cl.kvf_cond, cl.kvf_null, nullptr, nullptr, t, nullptr, false);
         } else if (fuse_cross) {
-          emit_ln_apply(prog, t, C, L, tn);
+          if (!cross_ln_done) emit_ln_apply(prog, t, C, L, tn);
           // row-major variant: the fused kernel streams fp32 K/V with cp.async in both tensor-core modes (tf32: rounded copy, bf16: the
           // fp32 cache); the null-branch pointer doubles as the "has a null branch" flag, so it is passed in the packed variant too
           const bool op_copy = pl.prec == MDT_PREC_TF32 && !packed;
           emit_gemm_attn(prog, tn, C, L, d_wq, d_bq, 1, layer, op_copy ? cl.kv_cond_op : (void*)cl.kv_cond,
                          op_copy ? cl.kv_null_op : (void*)cl.kv_null, cl.kvf_cond, cl.kvf_null);
         } else if (fast) {
-          emit_ln_apply(prog, t, C, L, tn);
+          if (!cross_ln_done) emit_ln_apply(prog, t, C, L, tn);
           emit_gemm_tma(prog, tn, C, L, 1, d_wq, d_bq, Hd, 0, nullptr, nullptr, pl.qc);
         } else {
           row_stats(prog, t, C, L, pl.row_stats);
@@ -793,7 +807,11 @@ struct Builder {
         } else if (fast) {
           emit_gemm_tma(prog, tn, C, L, 1, d_w0, d_b0, mid, 1, nullptr, nullptr, pl.ff);
           // the last block's output is consumed by to_out as a raw operand: write the copy here
-          emit_gemm_tma(prog, pl.ff, mid, L, 1, d_w2, d_b2, C, 0, t, t, (i == nblocks - 1) ? (void*)tn : nullptr);
+          // (other blocks: LayerNorm(t) for the next block's self-attention, from the same epilogue)
+          const bool last = i == nblocks - 1;
+          const bool ln_next = !last && ln_epilogue_ok(C);
+          emit_gemm_tma(prog, pl.ff, mid, L, 1, d_w2, d_b2, C, 0, t, t, (last || ln_next) ? (void*)tn : nullptr, 0, ln_next);
+          tn_is_ln = ln_next;
         } else {
           emit(prog, gemm_op(make_aload(ts, L, L, 1, 1, 0), d_w0, tc_copy(d_w0, (size_t)mid * C), d_b0, mid, 1, nullptr, pl.ff, L));
           Src fs{pl.ff, mid, nullptr, 0, 1.f};
@@ -1082,7 +1100,7 @@ static std::string describe(const Op& op, int Beff) {
   const char* h = op.half ? " half" : "";
   switch (op.type) {
     case OP_GEMM_TMA: snprintf(b, sizeof b, "gemm_tma  M=%d N=%d K=%dx%d L=%d bn=%d%s%s%s%s", Beff * op.rps, op.tg.N, op.tg.taps, op.tg.C, op.tg.L, op.tg.BN,
-                               op.tg.gn_L ? " +gn" : "", op.tg.res ? " +res" : "", op.tg.act ? " +act" : "", h); break;
+                               op.tg.gn_L ? " +gn" : "", op.tg.res ? " +res" : "", op.tg.act ? " +act" : (op.tg.cop_ln ? " +ln" : ""), h); break;
     case OP_GEMM_ATTN: snprintf(b, sizeof b, "gemm_attn%s %s M=%d C=%d L=%d%s", op.umma_core ? "_umma" : "", op.cross ? "cross" : "self", Beff * op.rps, op.gat.C, op.gat.L, h); break;
     case OP_ATTN_LAYER: snprintf(b, sizeof b, "attn_%s%s %s M=%d C=%d L=%d%s%s", op.frag ? "frag " : "layer", op.al.fused ? "" : "(unfused)", op.cross ? "cross" : "self", Beff * op.rps, op.al.a.C, op.al.a.L, op.al.Cop ? " +cop" : "", h); break;
     case OP_RESNET_SMALL: snprintf(b, sizeof b, "resnet_small %s B=%d L=%d %d->%d%s", op.rs.mode ? "head" : "full", Beff, op.rs.L, op.rs.Cin, op.rs.Cout, h); break;
