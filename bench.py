@@ -333,8 +333,9 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peaks, peak_src = measured_peaks()
-    if args.precision == "bf16":
-        peak, peak_note = peaks["bf16_tflops_sustained"], f"bf16 sustained, {peak_src}"
+    if args.precision in ("bf16", "fp16"):
+        # kind::f16 runs bf16 and fp16 operands at the same rate: the measured dense bf16 figure is the denominator for both
+        peak, peak_note = peaks["bf16_tflops_sustained"], f"bf16 sustained (kind::f16 rate), {peak_src}"
     elif args.precision == "tf32":
         peak, peak_note = cublas_peak_tflops("tf32"), "cuBLAS TF32 8192^3 best-of-10 measured in this run (MEASURED_PEAKS.json lists bf16 only)"
     else:
@@ -345,7 +346,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"tf32": "tf32 operands / f32 accumulate", "bf16": "bf16 operands / f32 accumulate", "fp32": "f32"}[args.precision],
+        "dtype": {"tf32": "tf32 operands / f32 accumulate", "bf16": "bf16 operands / f32 accumulate", "fp32": "f32",
+                  "fp16": "fp16 operands (11-bit significand, as tf32) / f32 accumulate"}[args.precision],
         "data": "synthetic", "config": dict(workload(name, B), precision=args.precision,
                                             parallelism=f"batch-sharded x{world}, no step-path collective"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * c["n_ctx"] * 4 + B * P * L * 4, "d2h_bytes_per_step": B * P * L * 4,
@@ -360,9 +362,10 @@ def run_ours(args):
                              "time of the region, per GPU; one 'launch' = one sample() pass (kernel shares in profiles/); traffic = summed ncu "
                              "dram__bytes of every kernel of one pass"},
     }
-    if args.also and args.also != args.precision:
-        # secondary arithmetic mode, same workload, device-resident timing only (reported beside the headline)
-        plan2 = model._plan_for(dev, args.also, batch=B, timesteps=T)
+    also = []
+    for other in [a for a in args.also.split(",") if a and a != args.precision]:
+        # secondary arithmetic modes, same workload, device-resident timing only (reported beside the headline)
+        plan2 = model._plan_for(dev, other, batch=B, timesteps=T)
         def step2(i):
             return plan2.sample(cond_dev, num_steps=T, sigma_schedule=sched, sampler=sampler, clamp=False,
                                 cond_scale=CS, seed=1234 + i, sample_offset=rank * B, return_tokens=tokens)
@@ -374,8 +377,14 @@ def run_ours(args):
         for i in range(2):
             step2(50 + i)
         f1.record(); torch.cuda.synchronize()
-        line["also"] = {"precision": args.also, "value": B * 2 / (f0.elapsed_time(f1) * 1e-3), "unit": UNIT,
-                        "note": "same workload in the looser-bound mode (per GPU); not the headline"}
+        also.append({"precision": other, "value": B * 2 / (f0.elapsed_time(f1) * 1e-3), "unit": UNIT,
+                     "note": "same workload in another arithmetic mode (per GPU); not the headline"})
+        for k in [k for k, v in model._plans.items() if v is plan2]:     # free its workspace before the next mode
+            del model._plans[k]
+        plan2.close()
+        del plan2
+    if also:
+        line["also"] = also
     if world == 1 and not args.no_cpu:
         _, sd, cfg = oracle_bundle(name)
         v, cores, kind, sample = cpu_reference_rate(name, sd, cfg, batch=args.ref_batch, tprime=args.ref_timesteps, repeats=1,
@@ -393,14 +402,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("MDT_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("MDT_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16", "fp16"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-batch", type=int, default=256)
     ap.add_argument("--ref-timesteps", type=int, default=5)
     ap.add_argument("--linearity", action="store_true", help="reference arm: add the full-length B=4 linearity check")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--also", default="bf16", help="secondary precision mode reported under 'also' ('' to skip)")
+    ap.add_argument("--also", default="tf32,bf16,fp16", help="other precision modes reported under 'also' (comma separated; '' to skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

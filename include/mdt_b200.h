@@ -39,7 +39,9 @@ typedef enum {
 typedef enum {
   MDT_PREC_FP32 = 0, /* CUDA-core fp32 FFMA: bit-for-bit-class parity mode            */
   MDT_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 accumulate in TMEM                   */
-  MDT_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM    */
+  MDT_PREC_BF16 = 2, /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM    */
+  MDT_PREC_F16 = 3   /* tcgen05 kind::f16 (fp16 operands: tf32's 11-bit significand in half the bytes, saturating at +-65504),
+                        fp32 accumulate in TMEM, fp32 residual stream / norms / sampler state */
 } mdt_precision;
 
 /* Static model description.  Mirrors the kwargs QMDiffusion / QMDiffusionForward pass to

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmdt_b200.so")
 MDT_ABI_VERSION = 1
 MDT_MAX_LEVELS = 4
-PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
+PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2, "fp16": 3}
 
 EXPORTS = [
     "mdt_last_error", "mdt_abi_version", "mdt_device_count", "mdt_adpm2_scalars", "mdt_aeuler_scalars", "mdt_karras_sigmas",

@@ -99,7 +99,7 @@ static int g_sms_attn = 0;
 // Returns false when the shape does not fit the two-stage shared-memory budget (caller falls back).
 static bool bulk_cfg(const AttnParams& p, int kind, BulkAttnCfg* c, size_t* smem) {
   if (p.d != 64 || p.nq > 64 || p.nk > 64 || p.nq < 1 || p.nk < 1) return false;
-  const int esz = kind == 2 ? 2 : 4, pad = kind == 2 ? 8 : 4;
+  const int esz = kind >= 2 ? 2 : 4, pad = kind >= 2 ? 8 : 4;
   const size_t limit = 98 * 1024;
   for (int HC = p.heads; HC >= 1; HC >>= 1) {
     if (p.heads % HC) continue;
@@ -120,7 +120,7 @@ static bool bulk_cfg(const AttnParams& p, int kind, BulkAttnCfg* c, size_t* smem
 bool attention_bulk_supported(const AttnParams& p, int kind) {
   BulkAttnCfg c; size_t smem;
   // every source segment must be 16-byte aligned for cp.async.bulk
-  const int esz = kind == 2 ? 2 : 4;
+  const int esz = kind >= 2 ? 2 : 4;
   if ((p.ldq * esz) % 16 || (p.ldkv * esz) % 16 || (p.d * esz) % 16) return false;
   return bulk_cfg(p, kind, &c, &smem);
 }
@@ -129,6 +129,7 @@ cudaError_t init_attention_bulk() {
   cudaError_t e = cudaFuncSetAttribute(attention_bulk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_bulk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   return e;
 }
 
@@ -145,7 +146,8 @@ cudaError_t launch_attention_bulk(const AttnParams& p, int kind, cudaStream_t s)
   const unsigned grid = (unsigned)(items < g_sms_attn ? items : g_sms_attn);
   if (kind == 0) attention_bulk_kernel<0><<<grid, 256, smem, s>>>(p, c);
   else if (kind == 1) attention_bulk_kernel<1><<<grid, 256, smem, s>>>(p, c);
-  else attention_bulk_kernel<2><<<grid, 256, smem, s>>>(p, c);
+  else if (kind == 2) attention_bulk_kernel<2><<<grid, 256, smem, s>>>(p, c);
+  else attention_bulk_kernel<3><<<grid, 256, smem, s>>>(p, c);
   return cudaGetLastError();
 }
 

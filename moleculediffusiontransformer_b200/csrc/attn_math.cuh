@@ -2,6 +2,7 @@
 // Shared by the streaming attention kernel (attention_bulk.cu) and the fused projection+attention kernel (gemm_attn.cu).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -34,6 +35,19 @@ template <> struct SmemIO<2> {
   static __device__ __forceinline__ float ld1(const T* p) { return __bfloat162float(*p); }
   static __device__ __forceinline__ void st(void* o, size_t i, float v) { reinterpret_cast<__nv_bfloat16*>(o)[i] = __float2bfloat16_rn(v); }
   static __device__ __forceinline__ void st2(void* o, size_t i, float a, float b) { *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(o) + i) = tc::pack_bf16(a, b); }
+};
+
+template <> struct SmemIO<3> {
+  typedef __half T;
+  static __device__ __forceinline__ float4 ld4(const T* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ float ld1(const T* p) { return __half2float(*p); }
+  static __device__ __forceinline__ void st(void* o, size_t i, float v) { reinterpret_cast<uint16_t*>(o)[i] = (uint16_t)(tc::pack_f16s(v, 0.f) & 0xffffu); }
+  static __device__ __forceinline__ void st2(void* o, size_t i, float a, float b) { *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(o) + i) = tc::pack_f16s(a, b); }
 };
 
 // One (sample, head): q rows at qs (stride sa), k rows at ks and v rows at vs (stride sb); ss = nq x (nk + 1) scratch.

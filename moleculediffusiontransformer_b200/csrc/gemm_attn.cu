@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();                                  // the set-up above overlaps the previous grid's tail (launch.cuh)
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
@@ -267,8 +268,9 @@ __global__ void __launch_bounds__(A_THREADS, 1) gemm_attn_kernel(const __grid_co
           for (int idx = lane; idx < p.nk * 16; idx += 32) {
             const int j = idx >> 4, c4 = (idx & 15) * 4;
             const size_t g = koff + (size_t)j * p.ldkv + (size_t)h * p.d + c4;
-            const float4 kk = SmemIO<2>::ld4(reinterpret_cast<const __nv_bfloat16*>(kb) + g);
-            const float4 vv = SmemIO<2>::ld4(reinterpret_cast<const __nv_bfloat16*>(kb) + g + p.heads * p.d);
+            typedef SmemIO<(KIND == 1 ? 2 : KIND)> KVIO;     // 2-byte cache in the operand type of the mode
+            const float4 kk = KVIO::ld4(reinterpret_cast<const typename KVIO::T*>(kb) + g);
+            const float4 vv = KVIO::ld4(reinterpret_cast<const typename KVIO::T*>(kb) + g + p.heads * p.d);
             *reinterpret_cast<float4*>(Kw + j * A_LD + c4) = kk;
             *reinterpret_cast<float4*>(Vw + j * A_LD + c4) = vv;
           }
@@ -307,14 +309,15 @@ bool gemm_attn_supported(int kind, int C, int L, int heads, int d, int cross, in
 
 typedef void (*GemmAttnKernel)(const CUtensorMap, const CUtensorMap, const GemmAttnParams, const uint32_t);
 static GemmAttnKernel gemm_attn_variant(int kind, int mode) {
-  static const GemmAttnKernel tab[2][4] = {
+  static const GemmAttnKernel tab[3][4] = {
       {tc::gemm_attn_kernel<1, 0>, tc::gemm_attn_kernel<1, 1>, tc::gemm_attn_kernel<1, 2>, tc::gemm_attn_kernel<1, 3>},
-      {tc::gemm_attn_kernel<2, 0>, tc::gemm_attn_kernel<2, 1>, tc::gemm_attn_kernel<2, 2>, tc::gemm_attn_kernel<2, 3>}};
-  return tab[kind == 1 ? 0 : 1][mode];
+      {tc::gemm_attn_kernel<2, 0>, tc::gemm_attn_kernel<2, 1>, tc::gemm_attn_kernel<2, 2>, tc::gemm_attn_kernel<2, 3>},
+      {tc::gemm_attn_kernel<3, 0>, tc::gemm_attn_kernel<3, 1>, tc::gemm_attn_kernel<3, 2>, tc::gemm_attn_kernel<3, 3>}};
+  return tab[kind - 1][mode];
 }
 
 cudaError_t init_gemm_attn() {
-  for (int kind = 1; kind <= 2; ++kind)
+  for (int kind = 1; kind <= 3; ++kind)
     for (int mode = 0; mode < 4; ++mode) {
       cudaError_t e = cudaFuncSetAttribute(gemm_attn_variant(kind, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
       if (e != cudaSuccess) return e;
@@ -334,15 +337,14 @@ cudaError_t launch_gemm_attn(const void* tmA, const void* tmB, const GemmAttnPar
   const int BN = p.cross ? p.d : 3 * p.d;
   const size_t smem = gemm_attn_smem(p, p.nk);
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
-  const uint32_t fmt = kind == 1 ? 2u : 1u;
+  const uint32_t fmt = tc::umma_fmt(kind);
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(tc::A_TM >> 4) << 24);
   const long long tiles = (long long)((p.M + tc::A_TM - 1) / tc::A_TM) * p.heads;
   const unsigned grid = (unsigned)(tiles < g_sms_ga ? tiles : g_sms_ga);
   const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(tmA);
   const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(tmB);
   const int mode = p.cross ? (p.kvf_c ? 3 : 2) : ((p.pack_self && p.L <= 8) ? 1 : 0);
-  gemm_attn_variant(kind, mode)<<<grid, tc::A_THREADS, smem, s>>>(a, b, p, idesc);
-  return cudaGetLastError();
+  return launch_k(gemm_attn_variant(kind, mode), grid, tc::A_THREADS, smem, s, a, b, p, idesc);
 }
 
 }  // namespace mdt

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();                                  // the set-up above overlaps the previous grid's tail (launch.cuh)
   const uint32_t tmem_base = tmem_base_s;       // columns [0, Cout): OUT accumulator; [Cout + b * BN, ...): two projection accumulators
 
   if (warp == 0) {
@@ -578,7 +579,7 @@ static bool attn_frag_config(int d, int cross, int Cout, int* nst, int* stage_by
 // Cout = 0 asks for the unfused variant (head outputs to the global attention tensor, out-projection elsewhere)
 bool attn_frag_supported(int kind, int C, int L, int heads, int d, int cross, int Cout) {
   const int kch = kind == 1 ? 32 : 64;
-  if (kind != 1 && kind != 2) return false;
+  if (kind < 1 || kind > 3) return false;
   if (d != 64 || heads < 2 || (heads & 1) || C % kch) return false;
   if (!(L == 4 || L == 8 || L == 16)) return false;
   if (Cout != 0 && (Cout < 128 || Cout > 256 || Cout % 128)) return false;   // four column quarters of >= 32 columns
@@ -590,16 +591,19 @@ typedef void (*AttnFragKernel)(const CUtensorMap, const CUtensorMap, const CUten
                                const uint32_t, const uint32_t);
 // mode: 0 self; 4 / 8 / 16 cross with that many query rows per sample
 static AttnFragKernel attn_frag_variant(int kind, int mode, int f16) {
-  static const AttnFragKernel tab[2][2][4] = {
+  // fp16 operands (kind 3) always run the f16 attention core
+  static const AttnFragKernel tab[3][2][4] = {
       {{tc::attn_frag_kernel<1, 0, 0>, tc::attn_frag_kernel<1, 4, 0>, tc::attn_frag_kernel<1, 8, 0>, tc::attn_frag_kernel<1, 16, 0>},
        {tc::attn_frag_kernel<1, 0, 1>, tc::attn_frag_kernel<1, 4, 1>, tc::attn_frag_kernel<1, 8, 1>, tc::attn_frag_kernel<1, 16, 1>}},
       {{tc::attn_frag_kernel<2, 0, 0>, tc::attn_frag_kernel<2, 4, 0>, tc::attn_frag_kernel<2, 8, 0>, tc::attn_frag_kernel<2, 16, 0>},
-       {tc::attn_frag_kernel<2, 0, 1>, tc::attn_frag_kernel<2, 4, 1>, tc::attn_frag_kernel<2, 8, 1>, tc::attn_frag_kernel<2, 16, 1>}}};
-  return tab[kind == 1 ? 0 : 1][f16 ? 1 : 0][mode == 0 ? 0 : (mode == 4 ? 1 : (mode == 8 ? 2 : 3))];
+       {tc::attn_frag_kernel<2, 0, 1>, tc::attn_frag_kernel<2, 4, 1>, tc::attn_frag_kernel<2, 8, 1>, tc::attn_frag_kernel<2, 16, 1>}},
+      {{tc::attn_frag_kernel<3, 0, 1>, tc::attn_frag_kernel<3, 4, 1>, tc::attn_frag_kernel<3, 8, 1>, tc::attn_frag_kernel<3, 16, 1>},
+       {tc::attn_frag_kernel<3, 0, 1>, tc::attn_frag_kernel<3, 4, 1>, tc::attn_frag_kernel<3, 8, 1>, tc::attn_frag_kernel<3, 16, 1>}}};
+  return tab[kind - 1][f16 ? 1 : 0][mode == 0 ? 0 : (mode == 4 ? 1 : (mode == 8 ? 2 : 3))];
 }
 
 cudaError_t init_attn_frag() {
-  for (int kind = 1; kind <= 2; ++kind)
+  for (int kind = 1; kind <= 3; ++kind)
     for (int mode : {0, 4, 8, 16})
       for (int f16 = 0; f16 < 2; ++f16) {
         cudaError_t e = cudaFuncSetAttribute(attn_frag_variant(kind, mode, f16), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Z_SMEM_LIMIT);
@@ -620,17 +624,15 @@ cudaError_t launch_attn_frag(const void* tmA, const void* tmB, const void* tmS, 
   p.nacc = 2;
   p.nslot = a.heads + tc::Z_LA;
   const int BN = a.cross ? a.d : 3 * a.d;
-  const uint32_t fmt = kind == 1 ? 2u : 1u;
+  const uint32_t fmt = tc::umma_fmt(kind);
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(tc::Z_TM >> 4) << 24);
   const uint32_t idesc_o = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(tc::Z_TM >> 4) << 24);
   const int nitems = ((a.M + tc::Z_TM - 1) / tc::Z_TM) * (p.fused ? 1 : a.heads);
   const int sms = attn_layer_sms();
   const unsigned grid = (unsigned)(nitems < sms ? nitems : sms);
-  attn_frag_variant(kind, a.cross ? a.L : 0, p.f16)<<<grid, tc::Z_THREADS, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(tmA),
-                                                                     *reinterpret_cast<const CUtensorMap*>(tmB),
-                                                                     *reinterpret_cast<const CUtensorMap*>(tmS),
-                                                                     *reinterpret_cast<const CUtensorMap*>(tmW), p, idesc, idesc_o);
-  return cudaGetLastError();
+  return launch_k(attn_frag_variant(kind, a.cross ? a.L : 0, p.f16), grid, tc::Z_THREADS, smem, s, *reinterpret_cast<const CUtensorMap*>(tmA),
+                  *reinterpret_cast<const CUtensorMap*>(tmB), *reinterpret_cast<const CUtensorMap*>(tmS),
+                  *reinterpret_cast<const CUtensorMap*>(tmW), p, idesc, idesc_o);
 }
 
 }  // namespace mdt

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(Y_THREADS, 1) attn_layer_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();                                  // the set-up above overlaps the previous grid's tail (launch.cuh)
   const uint32_t tmem_base = tmem_base_s;       // columns [0, Cout): OUT accumulator; [Cout + b * BN, ...): projection accumulators
 
   if (warp == 0) {
@@ -229,8 +230,8 @@ __global__ void __launch_bounds__(Y_THREADS, 1) attn_layer_kernel(const __grid_c
                     *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.Cop) + (size_t)mo * p.ldcop + no) =
                         make_uint4(to_tf32(o.x), to_tf32(o.y), to_tf32(o.z), to_tf32(o.w));
                   else
-                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.Cop) + (size_t)mo * p.ldcop + no) =
-                        make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+                    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.Cop) + (size_t)mo * p.ldcop + no) =
+                        make_uint2(pack_op2<KIND>(o.x, o.y), pack_op2<KIND>(o.z, o.w));
                 }
               }
             }
@@ -375,7 +376,7 @@ static bool attn_layer_config(int d, int cross, int Cout, int* nst, int* stage_b
 // cross != 0 needs the fragment-ordered K / V cache (packed path of gemm_attn.cu: L in {4, 8, 16}, n_ctx <= 16)
 bool attn_layer_supported(int kind, int C, int L, int heads, int d, int cross, int Cout) {
   const int kch = kind == 1 ? 32 : 64;
-  if (kind != 1 && kind != 2) return false;
+  if (kind < 1 || kind > 3) return false;
   if (d != 64 || heads < 2 || C % kch || L < 1 || L > 32 || (128 % L) != 0) return false;
   if (cross && !(L == 4 || L == 8 || L == 16)) return false;
   if (Cout < 32 || Cout > 256 || Cout % 32) return false;
@@ -392,14 +393,15 @@ size_t attn_layer_scratch_bytes(int kind, int heads, int d) {
 typedef void (*AttnLayerKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnLayerParams,
                                 const uint32_t, const uint32_t);
 static AttnLayerKernel attn_layer_variant(int kind, int mode) {
-  static const AttnLayerKernel tab[2][3] = {
+  static const AttnLayerKernel tab[3][3] = {
       {tc::attn_layer_kernel<1, 0>, tc::attn_layer_kernel<1, 1>, tc::attn_layer_kernel<1, 3>},
-      {tc::attn_layer_kernel<2, 0>, tc::attn_layer_kernel<2, 1>, tc::attn_layer_kernel<2, 3>}};
-  return tab[kind == 1 ? 0 : 1][mode == 3 ? 2 : mode];
+      {tc::attn_layer_kernel<2, 0>, tc::attn_layer_kernel<2, 1>, tc::attn_layer_kernel<2, 3>},
+      {tc::attn_layer_kernel<3, 0>, tc::attn_layer_kernel<3, 1>, tc::attn_layer_kernel<3, 3>}};
+  return tab[kind - 1][mode == 3 ? 2 : mode];
 }
 
 cudaError_t init_attn_layer() {
-  for (int kind = 1; kind <= 2; ++kind)
+  for (int kind = 1; kind <= 3; ++kind)
     for (int mode : {0, 1, 3}) {
       cudaError_t e = cudaFuncSetAttribute(attn_layer_variant(kind, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y_SMEM_LIMIT);
       if (e != cudaSuccess) return e;
@@ -417,18 +419,16 @@ cudaError_t launch_attn_layer(const void* tmA, const void* tmB, const void* tmS,
   if (a.cross && !a.kvf_c) return cudaErrorInvalidValue;
   p.nslot = a.heads + tc::Y_LA;
   const int BN = a.cross ? a.d : 3 * a.d;
-  const uint32_t fmt = kind == 1 ? 2u : 1u;
+  const uint32_t fmt = tc::umma_fmt(kind);
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(tc::Y_TM >> 4) << 24);
   const uint32_t idesc_o = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(tc::Y_TM >> 4) << 24);
   const int nblk = (a.M + tc::Y_TM - 1) / tc::Y_TM;
   const int sms = attn_layer_sms();
   const unsigned grid = (unsigned)(nblk < sms ? nblk : sms);
   const int mode = a.cross ? 3 : ((a.pack_self && a.L <= 8) ? 1 : 0);
-  attn_layer_variant(kind, mode)<<<grid, tc::Y_THREADS, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(tmA),
-                                                                   *reinterpret_cast<const CUtensorMap*>(tmB),
-                                                                   *reinterpret_cast<const CUtensorMap*>(tmS),
-                                                                   *reinterpret_cast<const CUtensorMap*>(tmW), p, idesc, idesc_o);
-  return cudaGetLastError();
+  return launch_k(attn_layer_variant(kind, mode), grid, tc::Y_THREADS, smem, s, *reinterpret_cast<const CUtensorMap*>(tmA),
+                  *reinterpret_cast<const CUtensorMap*>(tmB), *reinterpret_cast<const CUtensorMap*>(tmS),
+                  *reinterpret_cast<const CUtensorMap*>(tmW), p, idesc, idesc_o);
 }
 
 }  // namespace mdt

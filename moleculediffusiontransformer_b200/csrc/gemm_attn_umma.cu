@@ -326,6 +326,7 @@ static size_t gemm_attn_umma_smem(int cross) {
 bool gemm_attn_umma_supported(int kind, int C, int L, int heads, int d, int cross, int nk_max) {
   const int kch = kind == 1 ? 32 : 64;
   if (d != 64 || C % kch || L < 1 || L > 32 || (L & (L - 1))) return false;
+  if (kind == 3) return false;   // opt-in experiment: tf32 / bf16 operands only
   if (cross) return false;   // cross-attention stays on gemm_attn.cu (n_ctx key slots per sample would have to fit in L columns)
   (void)heads; (void)nk_max;
   return true;

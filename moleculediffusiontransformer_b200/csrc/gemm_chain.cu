@@ -38,7 +38,7 @@ __device__ __forceinline__ void store_op_f4(void* base, size_t idx, float4 v) {
   if (KIND == 1)
     *reinterpret_cast<uint4*>(reinterpret_cast<float*>(base) + idx) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
   else
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + idx) = make_uint2(pack_op2<KIND>(v.x, v.y), pack_op2<KIND>(v.z, v.w));
 }
 
 // NCH = 32-column chunks of the output tile per epilogue warp: 1 for C = 128, 2 for C = 256
@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) ff_chain_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();                                  // the set-up above overlaps the previous grid's tail (launch.cuh)
   const uint32_t tmem_base = tmem_base_s;        // columns [0, C): output accumulator; [C, C + 256): two first-GEMM accumulators
 
   if (warp == 0) {
@@ -337,7 +338,7 @@ static bool ff_chain_config(int C, int* nst, int* stage_bytes, unsigned* tmem_co
 
 bool ff_chain_supported(int kind, int C, int mid, int L) {
   const int kch = kind == 1 ? 32 : 64;
-  if (kind != 1 && kind != 2) return false;
+  if (kind < 1 || kind > 3) return false;
   if (C != 128 && C != 256) return false;                  // output tile = one UMMA of N = C; LayerNorm chunks per warp = C / 128
   if (mid % 128 || mid < 256 || mid > 2048 || C % kch) return false;
   if (L < 1 || L > 128 || (128 % L) != 0) return false;
@@ -352,6 +353,8 @@ cudaError_t init_ff_chain() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::ff_chain_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM_LIMIT);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::ff_chain_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM_LIMIT);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::ff_chain_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM_LIMIT);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::ff_chain_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM_LIMIT);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::ff_chain_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_SMEM_LIMIT);
   return e;
 }
 
@@ -361,7 +364,7 @@ cudaError_t launch_ff_chain(const void* tmA, const void* tmB0, const void* tmS, 
   if (p.M <= 0) return cudaSuccess;
   size_t smem = 0;
   if (!ff_chain_config(p.C, &p.nst, &p.stage_bytes, &p.tmem_cols, &smem)) return cudaErrorInvalidValue;
-  const uint32_t fmt = kind == 1 ? 2u : 1u;
+  const uint32_t fmt = tc::umma_fmt(kind);
   const uint32_t idesc1 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(tc::C_TM >> 4) << 24);
   const uint32_t idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.C >> 3) << 17) | ((uint32_t)(tc::C_TM >> 4) << 24);
   const int nblk = (p.M + tc::C_TM - 1) / tc::C_TM;
@@ -371,11 +374,10 @@ cudaError_t launch_ff_chain(const void* tmA, const void* tmB0, const void* tmS, 
   const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(tmB0);
   const CUtensorMap& sc = *reinterpret_cast<const CUtensorMap*>(tmS);
   const CUtensorMap& w = *reinterpret_cast<const CUtensorMap*>(tmW);
-  if (kind == 1 && p.C == 128) tc::ff_chain_kernel<1, 1><<<grid, tc::C_THREADS, smem, s>>>(a, b, sc, w, p, idesc1, idesc2);
-  else if (kind == 1) tc::ff_chain_kernel<1, 2><<<grid, tc::C_THREADS, smem, s>>>(a, b, sc, w, p, idesc1, idesc2);
-  else if (p.C == 128) tc::ff_chain_kernel<2, 1><<<grid, tc::C_THREADS, smem, s>>>(a, b, sc, w, p, idesc1, idesc2);
-  else tc::ff_chain_kernel<2, 2><<<grid, tc::C_THREADS, smem, s>>>(a, b, sc, w, p, idesc1, idesc2);
-  return cudaGetLastError();
+  auto kern = kind == 1 ? (p.C == 128 ? tc::ff_chain_kernel<1, 1> : tc::ff_chain_kernel<1, 2>)
+            : kind == 2 ? (p.C == 128 ? tc::ff_chain_kernel<2, 1> : tc::ff_chain_kernel<2, 2>)
+                        : (p.C == 128 ? tc::ff_chain_kernel<3, 1> : tc::ff_chain_kernel<3, 2>);
+  return launch_k(kern, grid, tc::C_THREADS, smem, s, a, b, sc, w, p, idesc1, idesc2);
 }
 
 }  // namespace mdt

@@ -30,7 +30,7 @@ constexpr int B_BYTES = 128 * 128; // up to BN = 128 rows
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
 
-template <int KIND>  // 1 = tf32 (32 elements per 128-byte chunk), 2 = bf16 (64 elements)
+template <int KIND>  // 1 = tf32 (32 elements per 128-byte chunk), 2 = bf16, 3 = fp16 (64 elements)
 __global__ void __launch_bounds__(160) gemm_tc_kernel(const GemmParams p, const int BN, const uint32_t idesc, const int num_chunks) {
   constexpr int KCH = (KIND == 1) ? 32 : 64;
   constexpr int ESZ = (KIND == 1) ? 4 : 2;
@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(160) gemm_tc_kernel(const GemmParams p, const 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();                                  // the set-up above overlaps the previous grid's tail (launch.cuh)
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp < 4) {
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(160) gemm_tc_kernel(const GemmParams p, const 
           float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
           if (row_ok && k < p.K) v0 = aload4(a, aff, rb, rlo, k);
           if (row_ok && k + 4 < p.K) v1 = aload4(a, aff, rb, rlo, k + 4);
-          uint4 o = make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+          uint4 o = make_uint4(pack_op2<KIND>(v0.x, v0.y), pack_op2<KIND>(v0.z, v0.w), pack_op2<KIND>(v1.x, v1.y), pack_op2<KIND>(v1.z, v1.w));
           *reinterpret_cast<uint4*>(sa + row_off + ((j ^ sw) << 4)) = o;
         }
       }
@@ -178,6 +179,11 @@ __global__ void convert_bf16_kernel(const float* __restrict__ in, __nv_bfloat16*
   if (i < n) out[i] = __float2bfloat16_rn(in[i]);
 }
 
+__global__ void convert_f16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint16_t)(pack_f16s(in[i], 0.f) & 0xffffu);
+}
+
 static int pick_bn(int N) {
   if (N % 128 == 0) return 128;
   if (N % 64 == 0) return 64;
@@ -198,14 +204,16 @@ cudaError_t convert_weights_tc(const float* W, void* Wtc, long long n, int kind,
   if (n <= 0) return cudaSuccess;
   const unsigned grid = (unsigned)((n + 255) / 256);
   if (kind == 1) tc::convert_tf32_kernel<<<grid, 256, 0, s>>>(W, reinterpret_cast<uint32_t*>(Wtc), n);
-  else tc::convert_bf16_kernel<<<grid, 256, 0, s>>>(W, reinterpret_cast<__nv_bfloat16*>(Wtc), n);
+  else if (kind == 2) tc::convert_bf16_kernel<<<grid, 256, 0, s>>>(W, reinterpret_cast<__nv_bfloat16*>(Wtc), n);
+  else tc::convert_f16_kernel<<<grid, 256, 0, s>>>(W, reinterpret_cast<uint16_t*>(Wtc), n);
   return cudaGetLastError();
 }
 
 cudaError_t init_gemm_tc() {
   cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(tc::gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+  return e;
 }
 
 cudaError_t launch_gemm_tc(const GemmParams& p, int kind, cudaStream_t s) {
@@ -216,12 +224,10 @@ cudaError_t launch_gemm_tc(const GemmParams& p, int kind, cudaStream_t s) {
   const int num_chunks = (p.K + kch - 1) / kch;
   // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6); a/b format [7,10)/[10,13): TF32 = 2, BF16 = 1;
   // K-major both; N >> 3 at [17,23); M >> 4 at [24,29)
-  const uint32_t fmt = kind == 1 ? 2u : 1u;
+  const uint32_t fmt = tc::umma_fmt(kind);
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(tc::TM >> 4) << 24);
   dim3 grid((p.M + tc::TM - 1) / tc::TM, p.N / BN);
-  if (kind == 1) tc::gemm_tc_kernel<1><<<grid, 160, tc::SMEM_BYTES, s>>>(p, BN, idesc, num_chunks);
-  else tc::gemm_tc_kernel<2><<<grid, 160, tc::SMEM_BYTES, s>>>(p, BN, idesc, num_chunks);
-  return cudaGetLastError();
+  return launch_k(kind == 1 ? tc::gemm_tc_kernel<1> : (kind == 2 ? tc::gemm_tc_kernel<2> : tc::gemm_tc_kernel<3>), grid, 160, tc::SMEM_BYTES, s, p, BN, idesc, num_chunks);
 }
 
 }  // namespace mdt

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_enter();                                  // set-up above overlaps the previous grid's tail (launch.cuh)
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
               const float nx = (o.x - mean) * rstd, ny = (o.y - mean) * rstd, nz = (o.z - mean) * rstd, nw = (o.w - mean) * rstd;
               const size_t off = (size_t)mo * p.ldcop + half * cols_per_half + u * 32 + cl;
               if (KIND == 1) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.Cop) + off) = make_uint4(to_tf32(nx), to_tf32(ny), to_tf32(nz), to_tf32(nw));
-              else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.Cop) + off) = make_uint2(pack_bf16(nx, ny), pack_bf16(nz, nw));
+              else *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.Cop) + off) = make_uint2(pack_op2<KIND>(nx, ny), pack_op2<KIND>(nz, nw));
             }
           }
         }
@@ -308,8 +309,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
                   *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.Cop) + (size_t)mo * p.ldcop + no) =
                       make_uint4(to_tf32(o.x), to_tf32(o.y), to_tf32(o.z), to_tf32(o.w));
                 else
-                  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.Cop) + (size_t)mo * p.ldcop + no) =
-                      make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+                  *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.Cop) + (size_t)mo * p.ldcop + no) =
+                      make_uint2(pack_op2<KIND>(o.x, o.y), pack_op2<KIND>(o.z, o.w));
               }
             }
             __syncwarp();
@@ -341,8 +342,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
                   *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.Cop) + (size_t)mo * p.ldcop + no) =
                       make_uint4(to_tf32(o.x), to_tf32(o.y), to_tf32(o.z), to_tf32(o.w));
                 } else {
-                  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.Cop) + (size_t)mo * p.ldcop + no) =
-                      make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+                  *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.Cop) + (size_t)mo * p.ldcop + no) =
+                      make_uint2(pack_op2<KIND>(o.x, o.y), pack_op2<KIND>(o.z, o.w));
                 }
               }
             }
@@ -400,12 +401,13 @@ int make_tmap_act(void* map128, const void* base, int kind, int C, int L, long l
   tc::EncodeTiledFn fn = tc::encode_fn();
   if (!fn) return -1;
   const int esz = kind == 1 ? 4 : 2, kch = kind == 1 ? 32 : 64;
+  const CUtensorMapDataType dt = kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (kind == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   const int Lb = L >= 128 ? 128 : L, Sb = L >= 128 ? 1 : 128 / L;
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)samples};
   cuuint64_t strides[2] = {(cuuint64_t)C * esz, (cuuint64_t)C * L * esz};
   cuuint32_t box[3] = {(cuuint32_t)kch, (cuuint32_t)Lb, (cuuint32_t)Sb};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(reinterpret_cast<CUtensorMap*>(map128), kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(map128), dt, 3,
                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
@@ -415,11 +417,12 @@ int make_tmap_weight(void* map128, const void* base, int kind, long long K, int 
   tc::EncodeTiledFn fn = tc::encode_fn();
   if (!fn) return -1;
   const int esz = kind == 1 ? 4 : 2, kch = kind == 1 ? 32 : 64;
+  const CUtensorMapDataType dt = kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (kind == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
   cuuint64_t strides[1] = {(cuuint64_t)K * esz};
   cuuint32_t box[2] = {(cuuint32_t)kch, (cuuint32_t)BN};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(reinterpret_cast<CUtensorMap*>(map128), kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(map128), dt, 2,
                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
@@ -431,6 +434,8 @@ cudaError_t init_gemm_tma() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tma_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tma_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   return e;
 }
 
@@ -446,7 +451,7 @@ cudaError_t launch_gemm_tma(const void* tmA, const void* tmB, const TmaGemmParam
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  const uint32_t fmt = kind == 1 ? 2u : 1u;
+  const uint32_t fmt = tc::umma_fmt(kind);
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(tc::T_TM >> 4) << 24);
   const long long tiles = (long long)((p.M + tc::T_TM - 1) / tc::T_TM) * (p.N / p.BN);
   const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);   // persistent: one CTA per SM
@@ -454,11 +459,11 @@ cudaError_t launch_gemm_tma(const void* tmA, const void* tmB, const TmaGemmParam
   const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(tmB);
   const int smem = p.BN > 128 ? tc::T_SMEM_BYTES_WIDE : tc::T_SMEM_BYTES;
   if (p.cop_ln) {
-    if (kind == 1) tc::gemm_tma_kernel<1, true><<<grid, tc::T_THREADS, smem, s>>>(a, b, p, idesc);
-    else tc::gemm_tma_kernel<2, true><<<grid, tc::T_THREADS, smem, s>>>(a, b, p, idesc);
-  } else if (kind == 1) tc::gemm_tma_kernel<1, false><<<grid, tc::T_THREADS, smem, s>>>(a, b, p, idesc);
-  else tc::gemm_tma_kernel<2, false><<<grid, tc::T_THREADS, smem, s>>>(a, b, p, idesc);
-  return cudaGetLastError();
+    return launch_k(kind == 1 ? tc::gemm_tma_kernel<1, true> : (kind == 2 ? tc::gemm_tma_kernel<2, true> : tc::gemm_tma_kernel<3, true>), grid,
+                    tc::T_THREADS, smem, s, a, b, p, idesc);
+  }
+  return launch_k(kind == 1 ? tc::gemm_tma_kernel<1, false> : (kind == 2 ? tc::gemm_tma_kernel<2, false> : tc::gemm_tma_kernel<3, false>), grid,
+                  tc::T_THREADS, smem, s, a, b, p, idesc);
 }
 
 }  // namespace mdt

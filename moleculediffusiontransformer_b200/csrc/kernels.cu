@@ -6,8 +6,12 @@
 //   * groupnorm/rownorm     two-pass statistics feeding the GEMM prologues
 //   * sampler kernels       fused ADPM2 / EDM / classifier-free-guidance update (HBM-bound)
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include "aload.cuh"
+
+// launch through launch_k_light() (launch.cuh: programmatic dependent launch); a failed launch returns its error
+#define MDT_CK_LAUNCH(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
 namespace mdt {
 
@@ -20,6 +24,7 @@ constexpr int APAD = 4, BPAD = 4;
 
 template <int VEC>
 __global__ void __launch_bounds__(256) gemm_fp32_kernel(const GemmParams p) {
+  pdl_enter();
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Bs[2][BK][BN + BPAD];
 
@@ -175,9 +180,7 @@ cudaError_t launch_gemm_fp32(const GemmParams& p, cudaStream_t s) {
   if (p.M <= 0 || p.N <= 0) return cudaSuccess;
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
   const bool vec = aload_vec4_ok(p.a) && (p.K % 4 == 0);
-  if (vec) gemm_fp32_kernel<4><<<grid, 256, 0, s>>>(p);
-  else gemm_fp32_kernel<1><<<grid, 256, 0, s>>>(p);
-  return cudaGetLastError();
+  return launch_k_light(vec ? gemm_fp32_kernel<4> : gemm_fp32_kernel<1>, grid, 256, 0, s, p);
 }
 
 // ================================================================================================
@@ -206,6 +209,20 @@ template <> struct AttnIO<2> {
     return make_float4(fa.x, fa.y, fb.x, fb.y);
   }
   static __device__ __forceinline__ void st(void* p, size_t i, float v) { reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v); }
+};
+
+template <> struct AttnIO<3> {
+  typedef __half T;
+  static __device__ __forceinline__ float4 ld4(const void* p, size_t i) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p) + i);
+    const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), fb = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  static __device__ __forceinline__ void st(void* p, size_t i, float v) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(v));
+    reinterpret_cast<uint16_t*>(p)[i] = (uint16_t)(r & 0xffffu);
+  }
 };
 
 template <int KIND>
@@ -335,6 +352,7 @@ cudaError_t init_kernels() {
   cudaError_t e = cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = init_prep();
   if (e == cudaSuccess) e = init_attention_bulk();
   if (e == cudaSuccess) e = init_step_kernels();
@@ -355,7 +373,8 @@ cudaError_t launch_attention(const AttnParams& p, int kind, cudaStream_t s) {
   const unsigned grid = (unsigned)((warps + wpc - 1) / wpc);
   if (kind == 0) attention_kernel<0><<<grid, wpc * 32, smem, s>>>(p, wpc);
   else if (kind == 1) attention_kernel<1><<<grid, wpc * 32, smem, s>>>(p, wpc);
-  else attention_kernel<2><<<grid, wpc * 32, smem, s>>>(p, wpc);
+  else if (kind == 2) attention_kernel<2><<<grid, wpc * 32, smem, s>>>(p, wpc);
+  else attention_kernel<3><<<grid, wpc * 32, smem, s>>>(p, wpc);
   return cudaGetLastError();
 }
 
@@ -431,6 +450,7 @@ cudaError_t launch_rownorm_stats(const NormStatsParams& p, cudaStream_t s) {
 __global__ void upsample_gather_kernel(const float* __restrict__ Y, const float* __restrict__ bias,
                                        const float* __restrict__ add, float* __restrict__ out, int B, int Lin,
                                        int Cout, int f) {
+  pdl_enter();
   const int c4 = Cout >> 2;
   const long long total = (long long)B * Lin * f * c4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -464,13 +484,14 @@ cudaError_t launch_upsample_gather(const float* Y, const float* bias, const floa
   if (Cout % 4) return cudaErrorInvalidValue;
   const long long total = (long long)B * Lin * f * (Cout / 4);
   if (total <= 0) return cudaSuccess;
-  upsample_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Y, bias, add, out, B, Lin, Cout, f);
+  MDT_CK_LAUNCH(launch_k_light(upsample_gather_kernel, (unsigned)((total + 255) / 256), 256, 0, s, Y, bias, add, out, B, Lin, Cout, f));
   return cudaGetLastError();
 }
 
 // Patcher: (b, c, l*p + q) -> (b, c*p + q, l); token-major: in[b][l*p + q][c] <-> out[b][l][c*p + q]
 __global__ void patch_permute_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int L,
                                      int C, int p, int to_patched) {
+  pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   // idx enumerates the patched tensor [b][l][c*p + q]
@@ -489,7 +510,7 @@ cudaError_t launch_patch_permute(const float* in, float* out, int B, int L, int 
                                  cudaStream_t s) {
   const long long total = (long long)B * L * C * p;
   if (total <= 0) return cudaSuccess;
-  patch_permute_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, total, L, C, p, to_patched);
+  MDT_CK_LAUNCH(launch_k_light(patch_permute_kernel, (unsigned)((total + 255) / 256), 256, 0, s, in, out, total, L, C, p, to_patched));
   return cudaGetLastError();
 }
 
@@ -532,6 +553,7 @@ cudaError_t launch_encode_cond(const float* seq, const float* w, const float* bi
 
 __global__ void time_features_kernel(const float* __restrict__ t, const float* __restrict__ w,
                                      float* __restrict__ out, int rows, int half) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int dim = 2 * half + 1;
   if (idx >= rows * dim) return;
@@ -552,12 +574,13 @@ __global__ void time_features_kernel(const float* __restrict__ t, const float* _
 cudaError_t launch_time_features(const float* t, const float* w, float* out, int rows, int half, cudaStream_t s) {
   const int total = rows * (2 * half + 1);
   if (total <= 0) return cudaSuccess;
-  time_features_kernel<<<(total + 127) / 128, 128, 0, s>>>(t, w, out, rows, half);
+  MDT_CK_LAUNCH(launch_k_light(time_features_kernel, (total + 127) / 128, 128, 0, s, t, w, out, rows, half));
   return cudaGetLastError();
 }
 
 __global__ void film_fold_kernel(const float* __restrict__ ss, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float* __restrict__ aff, int rows, int C) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * C) return;
   const int r = idx / C, c = idx - r * C;
@@ -571,7 +594,7 @@ cudaError_t launch_film_fold(const float* ss, const float* gamma, const float* b
                              cudaStream_t s) {
   const int total = rows * C;
   if (total <= 0) return cudaSuccess;
-  film_fold_kernel<<<(total + 255) / 256, 256, 0, s>>>(ss, gamma, beta, aff, rows, C);
+  MDT_CK_LAUNCH(launch_k_light(film_fold_kernel, (total + 255) / 256, 256, 0, s, ss, gamma, beta, aff, rows, C));
   return cudaGetLastError();
 }
 
@@ -655,6 +678,7 @@ cudaError_t launch_step_init(const float* noise0, float* x, float* xin, const It
 // KDiffusion_mod.denoise_fn (diffusion.py:809-814), UNetCFG1d mix (modules.py:1253), ADPM2Sampler.step (diffusion.py:506-514).
 template <int WHICH>
 __global__ void step_update_kernel(const StepParams p) {
+  pdl_enter();
   extern __shared__ float tile[];  // injected noise [P][L+1] (WHICH == 1 only)
   const int b = blockIdx.x;
   const int P = p.P, L = p.L, n = P * L;
@@ -729,12 +753,12 @@ __global__ void step_update_kernel(const StepParams p) {
 cudaError_t launch_step_update(int which, const StepParams& p, cudaStream_t s) {
   if (p.B <= 0) return cudaSuccess;
   if ((p.P * p.L) % 4) return cudaErrorInvalidValue;
-  if (which == 0) step_update_kernel<0><<<p.B, 256, 0, s>>>(p);
+  if (which == 0) MDT_CK_LAUNCH(launch_k_light(step_update_kernel<0>, p.B, 256, 0, s, p));
   else {
     const bool tile = p.run ? p.has_noise != 0 : p.noise != nullptr;
     const size_t smem = tile ? (size_t)p.P * (p.L + 1) * sizeof(float) : 0;
     if (smem > MDT_STEP_SMEM_MAX) return cudaErrorInvalidValue;
-    step_update_kernel<1><<<p.B, 256, smem, s>>>(p);
+    MDT_CK_LAUNCH(launch_k_light(step_update_kernel<1>, p.B, 256, smem, s, p));
   }
   return cudaGetLastError();
 }
@@ -752,6 +776,7 @@ cudaError_t launch_add_int(int* dst, int v, cudaStream_t s) { add_int_kernel<<<1
 // (B,P,L) -> token-major [B*L][P] scaled by mul; dup != 0 also writes the null-branch half.
 __global__ void to_token_major_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int P, int L,
                                       float mul, int dup) {
+  pdl_enter();
   const long long total = (long long)B * P * L;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -768,7 +793,7 @@ cudaError_t launch_to_token_major(const float* in, float* out, int B, int P, int
                                   cudaStream_t s) {
   const long long total = (long long)B * P * L;
   if (total <= 0) return cudaSuccess;
-  to_token_major_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, B, P, L, mul, dup);
+  MDT_CK_LAUNCH(launch_k_light(to_token_major_kernel, (unsigned)((total + 255) / 256), 256, 0, s, in, out, B, P, L, mul, dup));
   return cudaGetLastError();
 }
 
@@ -776,6 +801,7 @@ cudaError_t launch_to_token_major(const float* in, float* out, int B, int P, int
 // final transposition of the sampler state (cfg = 0, cond_scale ignored) with optional clamp via mul trick off.
 __global__ void cfg_mix_to_bpl_kernel(const float* __restrict__ net, float* __restrict__ out, int B, int P, int L,
                                       float cond_scale, int cfg) {
+  pdl_enter();
   const long long total = (long long)B * P * L;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -793,7 +819,7 @@ cudaError_t launch_cfg_mix_to_bpl(const float* net, float* out, int B, int P, in
                                   cudaStream_t s) {
   const long long total = (long long)B * P * L;
   if (total <= 0) return cudaSuccess;
-  cfg_mix_to_bpl_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(net, out, B, P, L, cond_scale, cfg);
+  MDT_CK_LAUNCH(launch_k_light(cfg_mix_to_bpl_kernel, (unsigned)((total + 255) / 256), 256, 0, s, net, out, B, P, L, cond_scale, cfg));
   return cudaGetLastError();
 }
 

@@ -5,6 +5,7 @@
 // sample, channels contiguous).  All contractions are then row-major GEMMs with M = B_eff * L.
 #pragma once
 #include <cuda_runtime.h>
+#include "launch.cuh"
 #include <stdint.h>
 
 namespace mdt {

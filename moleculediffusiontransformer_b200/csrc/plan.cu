@@ -210,10 +210,10 @@ struct Builder {
     pl.wused += bytes;
     return d;
   }
-  // tensor-core copy of a packed [N][K] matrix (tf32-rounded fp32 bits or bf16), when the mode needs it
+  // tensor-core copy of a packed [N][K] matrix (tf32-rounded fp32 bits, bf16 or fp16), when the mode needs it
   const void* tc_copy(const float* dW, size_t n) {
     if (pl.prec == MDT_PREC_FP32) return nullptr;
-    void* d = slab_alloc(n * (pl.prec == MDT_PREC_BF16 ? 2 : 4));
+    void* d = slab_alloc(n * (pl.prec >= MDT_PREC_BF16 ? 2 : 4));
     CK(convert_weights_tc(dW, d, (long long)n, pl.prec, 0));
     return d;
   }
@@ -308,7 +308,7 @@ struct Builder {
 
   // ---- TMA path helpers (tensor-core precisions only)
   bool tma() const { return pl.prec != MDT_PREC_FP32; }
-  int esz() const { return pl.prec == MDT_PREC_BF16 ? 2 : 4; }
+  int esz() const { return pl.prec >= MDT_PREC_BF16 ? 2 : 4; }
   void* op_off(void* base, size_t elems) const { return reinterpret_cast<char*>(base) + elems * (size_t)esz(); }
   bool tma_ok(int C, int L, int N) const { return tma() && gemm_tma_shape_ok(pl.prec, C, L, N); }
 
@@ -444,7 +444,8 @@ struct Builder {
       memset(op.tmC, 0, sizeof op.tmC); memset(op.tmD, 0, sizeof op.tmD);
     }
     op.frag = fused ? frag_ok(C, L, cross) : true;
-    { const char* hf = getenv("MDT_ATTN_F16"); y.f16 = (op.frag && !(hf && hf[0] == '0')) ? 1 : 0; }
+    // fp16 operands always take the f16 attention core (gemm_attn_frag.cu instantiates only that pairing)
+    { const char* hf = getenv("MDT_ATTN_F16"); y.f16 = (op.frag && (pl.prec == MDT_PREC_F16 || !(hf && hf[0] == '0'))) ? 1 : 0; }
     if (cross && cross_layer >= 0) pl.cross[cross_layer].kperm = op.frag ? (y.f16 ? 2 : 1) : 0;
     emit(prog, op);
   }
@@ -1355,7 +1356,7 @@ int mdt_plan_create(const mdt_config* cfg, const mdt_tensor* tensors, int64_t n_
   if (prop.major != 10) return fail(MDT_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
   if (cfg->num_levels < 1 || cfg->num_levels > MDT_MAX_LEVELS) return fail(MDT_ERR_INVALID, "num_levels out of range");
   if (cfg->max_batch < 1) return fail(MDT_ERR_INVALID, "max_batch must be >= 1");
-  if (cfg->precision < 0 || cfg->precision > 2) return fail(MDT_ERR_INVALID, "unknown precision %d", cfg->precision);
+  if (cfg->precision < 0 || cfg->precision > 3) return fail(MDT_ERR_INVALID, "unknown precision %d", cfg->precision);
   mdt_plan* pl = new mdt_plan();
   int prev_device = -1;
   cudaGetDevice(&prev_device);   // creation must not change the caller's current device

@@ -15,7 +15,7 @@ __device__ __forceinline__ void store_op4(void* base, size_t idx, float4 v) {
   if (KIND == 1) {
     *reinterpret_cast<uint4*>(reinterpret_cast<float*>(base) + idx) = make_uint4(tc::to_tf32(v.x), tc::to_tf32(v.y), tc::to_tf32(v.z), tc::to_tf32(v.w));
   } else {
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = make_uint2(tc::pack_bf16(v.x, v.y), tc::pack_bf16(v.z, v.w));
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + idx) = make_uint2(tc::pack_op2<KIND>(v.x, v.y), tc::pack_op2<KIND>(v.z, v.w));
   }
 }
 
@@ -31,6 +31,7 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 
 template <int KIND>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p, const int spc) {
+  pdl_enter();
   extern __shared__ __align__(16) float sm[];
   const int C = p.c0 + p.c1, L = p.L, LC = L * C, cpg = C / p.groups;
   float* data = sm;                                   // [spc][LC]
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p, co
 // two statistics passes and the apply pass, so the tensor is read exactly once and no shared memory or block barrier is used.
 template <int KIND, int MAXP>
 __global__ void __launch_bounds__(256) gn_apply_reg_kernel(const GnApplyParams p, const int seg, const int pieces) {
+  pdl_enter();
   const int C = p.c0 + p.c1, L = p.L, cpg = C / p.groups, q4 = cpg >> 2;   // q4 = float4 per row segment
   const int lane = threadIdx.x & 31;
   const int gpw = 32 / seg;                                               // (sample, group) items per warp
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(256) gn_apply_reg_kernel(const GnApplyParams p
 // (cpg | 128) and a slab must not straddle the two concatenated sources (c0 % 128 == 0).
 template <int KIND, int LMAX>
 __global__ void __launch_bounds__(256) gn_apply_slab_kernel(const GnApplyParams p) {
+  pdl_enter();
   const int C = p.c0 + p.c1, L = p.L, cpg = C / p.groups;
   const int lane = threadIdx.x & 31;
   const int slabs = C >> 7;
@@ -301,11 +304,13 @@ cudaError_t launch_gn_apply(const GnApplyParams& p, int kind, cudaStream_t s) {
     const long long cap = (long long)sms * 8;
     if (p.L <= 8 && blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-#define MDT_SLAB_LAUNCH(K, LM) gn_apply_slab_kernel<K, LM><<<(unsigned)blocks, 256, 0, s>>>(p)
+    cudaError_t e = cudaSuccess;
+#define MDT_SLAB_LAUNCH(K, LM) e = launch_k_light(gn_apply_slab_kernel<K, LM>, (unsigned)blocks, 256, 0, s, p)
     if (kind == 1) { if (p.L <= 4) MDT_SLAB_LAUNCH(1, 4); else if (p.L <= 8) MDT_SLAB_LAUNCH(1, 8); else MDT_SLAB_LAUNCH(1, 16); }
-    else { if (p.L <= 4) MDT_SLAB_LAUNCH(2, 4); else if (p.L <= 8) MDT_SLAB_LAUNCH(2, 8); else MDT_SLAB_LAUNCH(2, 16); }
+    else if (kind == 2) { if (p.L <= 4) MDT_SLAB_LAUNCH(2, 4); else if (p.L <= 8) MDT_SLAB_LAUNCH(2, 8); else MDT_SLAB_LAUNCH(2, 16); }
+    else { if (p.L <= 4) MDT_SLAB_LAUNCH(3, 4); else if (p.L <= 8) MDT_SLAB_LAUNCH(3, 8); else MDT_SLAB_LAUNCH(3, 16); }
 #undef MDT_SLAB_LAUNCH
-    return cudaGetLastError();
+    return e;
   }
   {
     const int cpg = C / p.groups;
@@ -318,23 +323,24 @@ cudaError_t launch_gn_apply(const GnApplyParams& p, int kind, cudaStream_t s) {
       const long long warps = (items + gpw - 1) / gpw;
       const unsigned grid = (unsigned)((warps + 7) / 8);
       const int ppl = (pieces + seg - 1) / seg;          // float4 pieces per lane: sizes the register arrays
-#define MDT_GN_LAUNCH(K, P) gn_apply_reg_kernel<K, P><<<grid, 256, 0, s>>>(p, seg, pieces)
+      cudaError_t e = cudaSuccess;
+#define MDT_GN_LAUNCH(K, P) e = launch_k_light(gn_apply_reg_kernel<K, P>, grid, 256, 0, s, p, seg, pieces)
       if (kind == 1) { if (ppl <= 1) MDT_GN_LAUNCH(1, 1); else if (ppl <= 2) MDT_GN_LAUNCH(1, 2); else if (ppl <= 4) MDT_GN_LAUNCH(1, 4); else MDT_GN_LAUNCH(1, 8); }
-      else { if (ppl <= 1) MDT_GN_LAUNCH(2, 1); else if (ppl <= 2) MDT_GN_LAUNCH(2, 2); else if (ppl <= 4) MDT_GN_LAUNCH(2, 4); else MDT_GN_LAUNCH(2, 8); }
+      else if (kind == 2) { if (ppl <= 1) MDT_GN_LAUNCH(2, 1); else if (ppl <= 2) MDT_GN_LAUNCH(2, 2); else if (ppl <= 4) MDT_GN_LAUNCH(2, 4); else MDT_GN_LAUNCH(2, 8); }
+      else { if (ppl <= 1) MDT_GN_LAUNCH(3, 1); else if (ppl <= 2) MDT_GN_LAUNCH(3, 2); else if (ppl <= 4) MDT_GN_LAUNCH(3, 4); else MDT_GN_LAUNCH(3, 8); }
 #undef MDT_GN_LAUNCH
-      return cudaGetLastError();
+      return e;
     }
   }
   const int spc = gn_spc(p.L, C);
   const size_t smem = ((size_t)spc * p.L * C + 2 * (size_t)spc * p.groups) * sizeof(float);
   const unsigned grid = (unsigned)((p.B + spc - 1) / spc);
-  if (kind == 1) gn_apply_kernel<1><<<grid, 256, smem, s>>>(p, spc);
-  else gn_apply_kernel<2><<<grid, 256, smem, s>>>(p, spc);
-  return cudaGetLastError();
+  return launch_k_light(kind == 1 ? gn_apply_kernel<1> : (kind == 2 ? gn_apply_kernel<2> : gn_apply_kernel<3>), grid, 256, smem, s, p, spc);
 }
 
 template <int KIND, int NV>   // NV = float4 per lane = C / 128 rounded up (register array size)
 __global__ void __launch_bounds__(256) ln_apply_kernel(const LnApplyParams p) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)(p.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 8 + warp;
   if (row >= p.rows) return;
@@ -373,17 +379,20 @@ cudaError_t launch_ln_apply(const LnApplyParams& p, int kind, cudaStream_t s) {
   if (p.C % 4 || p.C > 1024) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)((p.rows + 7) / 8);
   const int nv = (p.C + 127) / 128;
-#define MDT_LN_LAUNCH(K, N) ln_apply_kernel<K, N><<<grid, 256, 0, s>>>(p)
+  cudaError_t e = cudaSuccess;
+#define MDT_LN_LAUNCH(K, N) e = launch_k_light(ln_apply_kernel<K, N>, grid, 256, 0, s, p)
   if (kind == 1) { if (nv <= 1) MDT_LN_LAUNCH(1, 1); else if (nv <= 2) MDT_LN_LAUNCH(1, 2); else if (nv <= 4) MDT_LN_LAUNCH(1, 4); else MDT_LN_LAUNCH(1, 8); }
-  else { if (nv <= 1) MDT_LN_LAUNCH(2, 1); else if (nv <= 2) MDT_LN_LAUNCH(2, 2); else if (nv <= 4) MDT_LN_LAUNCH(2, 4); else MDT_LN_LAUNCH(2, 8); }
+  else if (kind == 2) { if (nv <= 1) MDT_LN_LAUNCH(2, 1); else if (nv <= 2) MDT_LN_LAUNCH(2, 2); else if (nv <= 4) MDT_LN_LAUNCH(2, 4); else MDT_LN_LAUNCH(2, 8); }
+  else { if (nv <= 1) MDT_LN_LAUNCH(3, 1); else if (nv <= 2) MDT_LN_LAUNCH(3, 2); else if (nv <= 4) MDT_LN_LAUNCH(3, 4); else MDT_LN_LAUNCH(3, 8); }
 #undef MDT_LN_LAUNCH
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t init_prep() {
   cudaError_t e = cudaFuncSetAttribute(gn_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gn_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_apply_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  return e;
 }
 
 }  // namespace mdt

@@ -79,6 +79,7 @@ template <int WPS, int MT>
 __global__ void __launch_bounds__(RS_THREADS) resnet_small_kernel(const ResnetSmallParams p) {
   extern __shared__ __align__(16) float rs_smem[];
   __shared__ float red[4];
+  pdl_enter();
   constexpr int TPS = 32 * WPS, SPC = 4 / WPS;
   constexpr int L = 16 * MT, LP = L + 2 * RS_HALO;
   const int Cin = p.Cin, Cout = p.Cout;
@@ -228,7 +229,8 @@ __global__ void __launch_bounds__(RS_THREADS) resnet_small_kernel(const ResnetSm
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
               const size_t o = ((size_t)b * L + 16 * mt + g + 8 * rr) * Cout + co_base + 8 * nt + 2 * q;
-              if (p.kind == 2) *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.a2op) + o) = tc::pack_bf16(h[mt][nt][2 * rr], h[mt][nt][2 * rr + 1]);
+              if (p.kind >= 2) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.a2op) + o) =
+                  p.kind == 3 ? tc::pack_f16s(h[mt][nt][2 * rr], h[mt][nt][2 * rr + 1]) : tc::pack_bf16(h[mt][nt][2 * rr], h[mt][nt][2 * rr + 1]);
               else *reinterpret_cast<uint2*>(reinterpret_cast<float*>(p.a2op) + o) = make_uint2(tc::to_tf32(h[mt][nt][2 * rr]), tc::to_tf32(h[mt][nt][2 * rr + 1]));
               *reinterpret_cast<float2*>(p.out + o) = make_float2(sk[mt][nt][2 * rr], sk[mt][nt][2 * rr + 1]);
             }
@@ -327,8 +329,7 @@ cudaError_t launch_resnet_small(const ResnetSmallParams& p, cudaStream_t s) {
   const int spc = 4 / wps;
   const long long need = ((long long)p.B + spc - 1) / spc, want = (long long)g_sms_rs * per_sm;
   const unsigned grid = (unsigned)(need < want ? need : want);
-  resnet_small_variant(wps, p.L)<<<grid, RS_THREADS, smem, s>>>(p);
-  return cudaGetLastError();
+  return launch_k(resnet_small_variant(wps, p.L), grid, RS_THREADS, smem, s, p);
 }
 
 }  // namespace mdt

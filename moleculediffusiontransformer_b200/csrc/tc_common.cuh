@@ -1,6 +1,7 @@
 // tc_common.cuh -- inline-PTX helpers shared by the tcgen05 kernels (mbarrier, proxy fences, TMEM, UMMA, TMA).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace mdt {
@@ -132,6 +133,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// fp16 operands (kind 3): the same 11-bit significand as tf32 in half the bytes; the 5-bit exponent is covered by saturating at
+// +-65504 (operands here are normalised activations, post-activation values and weights: orders of magnitude inside the range)
+__device__ __forceinline__ uint32_t pack_f16s(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// two values -> one 32-bit pair of the 2-byte operand type of KIND (2 = bf16, 3 = fp16)
+template <int KIND>
+__device__ __forceinline__ uint32_t pack_op2(float lo, float hi) { return KIND == 3 ? pack_f16s(lo, hi) : pack_bf16(lo, hi); }
+// instruction-descriptor operand format of a kind (cute::UMMA: F16 = 0, BF16 = 1, TF32 = 2)
+__host__ __device__ inline uint32_t umma_fmt(int kind) { return kind == 1 ? 2u : (kind == 3 ? 0u : 1u); }
 
 
 // ---- L2 residency hints for the CTA-private scratch (rewritten every block, read back by TMA a few microseconds later) ----------

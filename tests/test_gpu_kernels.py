@@ -9,14 +9,14 @@ pytestmark = pytest.mark.gpu
 
 SHAPES = [(256, 128, 128), (1000, 512, 256), (4096, 1536, 128), (130, 64, 576), (257, 256, 1152), (96, 16, 48), (77, 1, 3),
           (64, 22, 66)]
-TOL = {"fp32": 2e-6, "tf32": 6e-4, "bf16": 5e-3}   # relative L2 vs float64; operand rounding 2^-11 / 2^-8
+TOL = {"fp32": 2e-6, "tf32": 6e-4, "bf16": 5e-3, "fp16": 6e-4}   # relative L2 vs float64; operand rounding 2^-11 / 2^-8
 
 
 def _rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm())
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16", "fp16"])
 @pytest.mark.parametrize("act", [0, 1])
 def test_linear_against_float64(prec, act):
     from moleculediffusiontransformer_b200 import _capi
