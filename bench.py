@@ -402,7 +402,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("MDT_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16", "fp16"])
+    ap.add_argument("--precision", default=os.environ.get("MDT_PRECISION", "fp16"), choices=["fp32", "tf32", "bf16", "fp16"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-batch", type=int, default=256)

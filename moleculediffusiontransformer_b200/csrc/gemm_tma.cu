@@ -151,23 +151,24 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
       if (LN) {
         // ---- LayerNorm epilogue (launcher guarantees N == BN in {128, 256}: a row block holds whole rows, four warps per quadrant
         // own 32 or 64 columns each).  C32 = acc + bias (+ res); Cop = (C32 - mean) * rstd, no affine (folded into the consumer's
-        // weights).  Two-pass statistics on the register copy: exact mean / centred M2 per 32-column chunk inside the eight lanes
-        // that hold it, equal-count Chan merges across chunks and across the four warps (one named barrier per tile).
+        // weights).  Exact mean / centred M2 per 32-column chunk inside the eight lanes that hold it, equal-count Chan merges across
+        // chunks and across the four warps (one named barrier per tile).
         const int nch = cols_per_half >> 5;          // 1 or 2 chunks of 32 columns per warp
         const int cl = (lane & 7) * 4, r0 = lane >> 3;
         const int m0 = mt * T_TM + q * 32;
-        float4 r[2][8];
+        float4 r[8];
         auto load_res = [&](int u) {
           const int no = half * cols_per_half + u * 32 + cl;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int mo = m0 + r0 + i * 4;
-            r[u][i] = (p.res && mo < p.M) ? *reinterpret_cast<const float4*>(p.res + (size_t)mo * p.ldres + no) : make_float4(0.f, 0.f, 0.f, 0.f);
+            r[i] = (p.res && mo < p.M) ? *reinterpret_cast<const float4*>(p.res + (size_t)mo * p.ldres + no) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         };
         load_res(0);                                 // ahead of the accumulator wait: the residual's latency hides behind it
         mbar_wait(&acc_full[buf], aphase);
         tc_fence_after();
+        float mean_w[8], m2_w[8];                    // per row of this lane: statistics over this warp's columns
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           if (u < nch) {
@@ -180,63 +181,65 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tma_kernel(const __grid_con
                 *reinterpret_cast<uint4*>(stg + lane * T_STG_LD + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
             __syncwarp();
-            if (u > 0) load_res(u);      // after the staging registers are dead (register budget: 576 threads)
+            if (u > 0) load_res(u);      // after the staging registers are dead (register budget: 576 threads = 96 per thread)
             const int no = col0 + cl;
             const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + no)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int mo = m0 + r0 + i * 4;
               float4 o = *reinterpret_cast<const float4*>(stg + (r0 + i * 4) * T_STG_LD + cl);
-              o.x += bv.x + r[u][i].x; o.y += bv.y + r[u][i].y; o.z += bv.z + r[u][i].z; o.w += bv.w + r[u][i].w;
-              r[u][i] = o;
-              if (p.C32 && mo < p.M) *reinterpret_cast<float4*>(p.C32 + (size_t)mo * p.ldc + no) = o;
-            }
-            __syncwarp();
-          }
-        }
-        // the accumulator lives in registers now: hand it back before the statistics exchange
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        float2* xb = xch + (size_t)(it & 1) * T_TM * 4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float mean_w = 0.f, m2_w = 0.f, mean0 = 0.f;
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (u < nch) {
-              const float4 o = r[u][i];
+              o.x += bv.x + r[i].x; o.y += bv.y + r[i].y; o.z += bv.z + r[i].z; o.w += bv.w + r[i].w;
+              if (mo < p.M) *reinterpret_cast<float4*>(p.C32 + (size_t)mo * p.ldc + no) = o;
+              // exact mean / centred M2 of this 32-column chunk inside the eight lanes that hold the row
               float sm = (o.x + o.y) + (o.z + o.w);
               sm += __shfl_xor_sync(0xffffffffu, sm, 1); sm += __shfl_xor_sync(0xffffffffu, sm, 2); sm += __shfl_xor_sync(0xffffffffu, sm, 4);
               const float mean = sm * (1.0f / 32.0f);
               const float dx = o.x - mean, dy = o.y - mean, dz = o.z - mean, dw = o.w - mean;
               float m2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
               m2 += __shfl_xor_sync(0xffffffffu, m2, 1); m2 += __shfl_xor_sync(0xffffffffu, m2, 2); m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
-              if (u == 0) { mean_w = mean; m2_w = m2; mean0 = mean; }
-              else { const float dm = mean - mean0; mean_w = 0.5f * (mean0 + mean); m2_w = m2_w + m2 + 16.0f * dm * dm; }
+              if (u == 0) { mean_w[i] = mean; m2_w[i] = m2; }
+              else { const float dm = mean - mean_w[i]; mean_w[i] = 0.5f * (mean_w[i] + mean); m2_w[i] = m2_w[i] + m2 + 16.0f * dm * dm; }
             }
+            __syncwarp();
           }
-          if ((lane & 7) == 0) xb[(q * 32 + r0 + i * 4) * 4 + half] = make_float2(mean_w, m2_w);
+        }
+        // the accumulator has been consumed: hand it back before the statistics exchange
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        float2* xb = xch + (size_t)(it & 1) * T_TM * 4;
+        if ((lane & 7) == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xb[(q * 32 + r0 + i * 4) * 4 + half] = make_float2(mean_w[i], m2_w[i]);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");      // the four column-group warps of this quadrant
+        // second pass: the values come back from C32 (this thread's own stores, L2-resident) instead of living in 64 registers
         const float inv_n = 1.0f / (float)p.N, n_w = (float)cols_per_half;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 e01 = *reinterpret_cast<const float4*>(xb + (q * 32 + r0 + i * 4) * 4);
-          const float4 e23 = *reinterpret_cast<const float4*>(xb + (q * 32 + r0 + i * 4) * 4 + 2);
-          const float mean = 0.25f * ((e01.x + e01.z) + (e23.x + e23.z));
-          const float d0 = e01.x - mean, d1 = e01.z - mean, d2 = e23.x - mean, d3 = e23.z - mean;
-          const float dev = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
-          const float rstd = rsqrtf(fmaf(n_w, dev, (e01.y + e01.w) + (e23.y + e23.w)) * inv_n + p.ln_eps);
-          const int mo = m0 + r0 + i * 4;
+        for (int u = 0; u < 2; ++u) {
+          if (u < nch) {
+            const int no = half * cols_per_half + u * 32 + cl;
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (u < nch && mo < p.M) {
-              const float4 o = r[u][i];
-              const float nx = (o.x - mean) * rstd, ny = (o.y - mean) * rstd, nz = (o.z - mean) * rstd, nw = (o.w - mean) * rstd;
-              const size_t off = (size_t)mo * p.ldcop + half * cols_per_half + u * 32 + cl;
-              if (KIND == 1) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.Cop) + off) = make_uint4(to_tf32(nx), to_tf32(ny), to_tf32(nz), to_tf32(nw));
-              else *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.Cop) + off) = make_uint2(pack_op2<KIND>(nx, ny), pack_op2<KIND>(nz, nw));
+            for (int i = 0; i < 8; ++i) {
+              const int mo = m0 + r0 + i * 4;
+              r[i] = mo < p.M ? *reinterpret_cast<const float4*>(p.C32 + (size_t)mo * p.ldc + no) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 e01 = *reinterpret_cast<const float4*>(xb + (q * 32 + r0 + i * 4) * 4);
+              const float4 e23 = *reinterpret_cast<const float4*>(xb + (q * 32 + r0 + i * 4) * 4 + 2);
+              const float mean = 0.25f * ((e01.x + e01.z) + (e23.x + e23.z));
+              const float d0 = e01.x - mean, d1 = e01.z - mean, d2 = e23.x - mean, d3 = e23.z - mean;
+              const float dev = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+              const float rstd = rsqrtf(fmaf(n_w, dev, (e01.y + e01.w) + (e23.y + e23.w)) * inv_n + p.ln_eps);
+              const int mo = m0 + r0 + i * 4;
+              if (mo < p.M) {
+                const float4 o = r[i];
+                const float nx = (o.x - mean) * rstd, ny = (o.y - mean) * rstd, nz = (o.z - mean) * rstd, nw = (o.w - mean) * rstd;
+                const size_t off = (size_t)mo * p.ldcop + no;
+                if (KIND == 1) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.Cop) + off) = make_uint4(to_tf32(nx), to_tf32(ny), to_tf32(nz), to_tf32(nw));
+                else *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.Cop) + off) = make_uint2(pack_op2<KIND>(nx, ny), pack_op2<KIND>(nz, nw));
+              }
             }
           }
         }
@@ -444,7 +447,7 @@ static int g_num_sms = 0;
 cudaError_t launch_gemm_tma(const void* tmA, const void* tmB, const TmaGemmParams& p, int kind, cudaStream_t s) {
   if (p.M <= 0 || p.N <= 0) return cudaSuccess;
   if (p.BN <= 0 || p.N % p.BN) return cudaErrorInvalidValue;
-  if (p.cop_ln && (p.N != p.BN || p.BN < 128 || !p.Cop || p.gn_L > 0 || p.act != 0)) return cudaErrorInvalidValue;
+  if (p.cop_ln && (p.N != p.BN || p.BN < 128 || !p.Cop || !p.C32 || p.gn_L > 0 || p.act != 0)) return cudaErrorInvalidValue;
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
