@@ -74,7 +74,7 @@ class _QMBase(nn.Module):
     def _plan_for(self, device: torch.device, precision: Optional[str] = None, batch: Optional[int] = None,
                   timesteps: int = 0):
         """One cached plan per (device, precision).  The workspace is sized for a power-of-two chunk that covers `batch`
-        (capped at MDT_MAX_BATCH, default 4096); a larger request rebuilds the plan, a smaller one reuses it."""
+        (capped at MDT_MAX_BATCH, default 32 rows per SM); a larger request rebuilds the plan, a smaller one reuses it."""
         from .plan import SamplerPlan, default_max_batch, default_precision
 
         precision = precision or default_precision()
@@ -84,7 +84,7 @@ class _QMBase(nn.Module):
         key = (index, precision)
         plan = self._plans.get(key)
         version = self._weights_fingerprint()
-        cap = default_max_batch()
+        cap = default_max_batch(device)
         want = cap if batch is None else min(cap, max(8, 1 << (max(int(batch), 1) - 1).bit_length()))
         steps = max(256, 1 << (max(int(timesteps), 2) - 1).bit_length())      # FiLM tables are sized per denoiser call
         if plan is None or plan.weights_version != version or plan.max_batch < want or plan.max_timesteps < timesteps:

@@ -26,8 +26,16 @@ def default_precision() -> str:
     return os.environ.get("MDT_PRECISION", "fp16")
 
 
-def default_max_batch() -> int:
-    return int(os.environ.get("MDT_MAX_BATCH", "4096"))
+def default_max_batch(device=None) -> int:
+    """Rows per chunk of a long sweep (one plan workspace, one graph replay per chunk).  MDT_MAX_BATCH if set; otherwise 32 rows per
+    SM (4736 on a 148-SM B200): the level-2 GEMMs see 8 B / 128 row blocks, and with B = 32 x SMs every level of the README
+    architecture is a whole number of waves (296 / 1184 / 4736 row blocks), where B = 4096 leaves the 256-block level at 1.73 waves."""
+    env = os.environ.get("MDT_MAX_BATCH")
+    if env:
+        return int(env)
+    if torch.cuda.is_available():
+        return 32 * torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
+    return 4096
 
 
 def make_config(model, precision: str, max_batch: int, max_timesteps: int) -> _capi.MdtConfig:
@@ -71,7 +79,7 @@ class SamplerPlan:
         self.device = device
         self.index = device.index if device.index is not None else torch.cuda.current_device()
         self.precision = precision or default_precision()
-        self.max_batch = max_batch or default_max_batch()
+        self.max_batch = max_batch or default_max_batch(device)
         self.max_timesteps = max_timesteps
         self.sigma_data = model.diffusion.diffusion.sigma_data
         self.pred_dim, self.max_length = model.pred_dim, model.max_length
