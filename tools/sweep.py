@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=65536, help="rows generated / sampled per call on each rank")
     ap.add_argument("--cond-scale", type=float, default=5.0)
     ap.add_argument("--timesteps", type=int, default=64)
-    ap.add_argument("--precision", default="tf32")
+    ap.add_argument("--precision", default=None, help="default: the package default (fp16 operands)")
     ap.add_argument("--seed", type=int, default=4)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
