@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ __align__(8) uint64_t att_ready, out_full, out_empty;
+  __shared__ __align__(8) uint64_t ln_bar[4];       // cop_ln: per TMEM lane quadrant, "row statistics of this block are in shared memory"
   __shared__ uint32_t tmem_base_s;
 
   uint8_t* smem = smem_raw;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
     mbar_init(&att_ready, Z_EPI_WARPS * 32);
     mbar_init(&out_full, 1);
     mbar_init(&out_empty, Z_EPI_WARPS);
+    for (int s = 0; s < 4; ++s) mbar_init(&ln_bar[s], 4);      // the four warps that share a quadrant's rows (column quarters)
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -296,11 +298,18 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
     const uint32_t lane_addr = (uint32_t)r16 << 16;
     const int sub = gp * 2 + half;          // this warp's column quarter of the OUT tile (four warps per quadrant)
     const uint64_t l2pol = p.l2_hint ? l2_policy_evict_last() : 0;
+    // cop_ln: LayerNorm(row) of the layer output as the operand copy.  First pass (final_epilogue): every warp leaves (mean, M2) of its
+    // column quarter per row in shared memory, double buffered by block parity; second pass (ln_pass2) one head later -- by then the
+    // other warp group has long finished its first pass, so the mbarrier wait costs nothing -- merges the four quarters and normalises
+    // the values it re-reads from its own C32 stores.
+    float2* xch = reinterpret_cast<float2*>(smem + NST * stage_bytes + (CROSS ? 0 : (size_t)Z_EPI_WARPS * 16 * Z_VLD * 4));   // [2][128][4]
+    const bool cop_ln = !CROSS && p.cop_ln != 0;     // self-attention layers only (the cross layer hands FeedForward a raw copy)
 
     auto final_epilogue = [&](int kk) {
       const int m0 = block_of_k(kk) * Z_TM + qd * 32;      // first token row of this warp's quadrant
       const int cols_w = Cout >> 2;
       bool waited = false;
+      float mean_w[2][2], m2_w[2][2];                      // cop_ln: statistics of rows {g, g + 8} + 16 hh over this warp's columns
       for (int cc = 0; cc < cols_w; cc += 32) {
         const int col0 = sub * cols_w + cc;
         // residual first (its HBM latency hides behind the accumulator wait): rows {g, g + 8} + 16 * hh, column pairs 8c + 2q
@@ -332,15 +341,88 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
                 const float ox = __uint_as_float(v[4 * c + 2 * rr]) + bv.x + r[hh][rr][c].x;
                 const float oy = __uint_as_float(v[4 * c + 2 * rr + 1]) + bv.y + r[hh][rr][c].y;
                 if (p.C32) *reinterpret_cast<float2*>(p.C32 + (size_t)mo * p.ldc + no) = make_float2(ox, oy);
-                if (p.Cop) SmemIO<KIND>::st2(p.Cop, (size_t)mo * p.ldcop + no, ox, oy);
+                if (p.Cop && !cop_ln) SmemIO<KIND>::st2(p.Cop, (size_t)mo * p.ldcop + no, ox, oy);
+                r[hh][rr][c] = make_float2(ox, oy);
+              } else {
+                r[hh][rr][c] = make_float2(0.f, 0.f);
               }
             }
           }
         }
+        if (cop_ln) {
+          // exact mean / centred M2 of this 32-column chunk: eight values per row in each of the four lanes of a quad
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              float sm = 0.f;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) sm += r[hh][rr][c].x + r[hh][rr][c].y;
+              sm += __shfl_xor_sync(0xffffffffu, sm, 1); sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+              const float mean = sm * (1.0f / 32.0f);
+              float m2 = 0.f;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) { const float dx = r[hh][rr][c].x - mean, dy = r[hh][rr][c].y - mean; m2 = fmaf(dx, dx, fmaf(dy, dy, m2)); }
+              m2 += __shfl_xor_sync(0xffffffffu, m2, 1); m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+              if (cc == 0) { mean_w[hh][rr] = mean; m2_w[hh][rr] = m2; }
+              else {       // second chunk (Cout = 256): equal-count merge
+                const float dm = mean - mean_w[hh][rr];
+                mean_w[hh][rr] = 0.5f * (mean_w[hh][rr] + mean); m2_w[hh][rr] = m2_w[hh][rr] + m2 + 16.0f * dm * dm;
+              }
+            }
+        }
+      }
+      if (cop_ln) {
+        float2* xb = xch + (size_t)(kk & 1) * Z_TM * 4;
+        if (q == 0) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) xb[(qd * 32 + hh * 16 + rr * 8 + g) * 4 + sub] = make_float2(mean_w[hh][rr], m2_w[hh][rr]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ln_bar[qd]);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&out_empty);
+    };
+
+    auto ln_pass2 = [&](int kk) {
+      const int m0 = block_of_k(kk) * Z_TM + qd * 32;
+      const int cols_w = Cout >> 2;
+      const float2* xb = xch + (size_t)(kk & 1) * Z_TM * 4;
+      const float inv_n = 1.0f / (float)Cout, n_w = (float)cols_w;
+      for (int cc = 0; cc < cols_w; cc += 32) {
+        const int col0 = sub * cols_w + cc;
+        float2 o[2][2][4];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int mo = m0 + hh * 16 + rr * 8 + g;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              o[hh][rr][c] = mo < a.M ? *reinterpret_cast<const float2*>(p.C32 + (size_t)mo * p.ldc + col0 + 8 * c + 2 * q) : make_float2(0.f, 0.f);
+          }
+        if (cc == 0) mbar_wait(&ln_bar[qd], (uint32_t)kk & 1u);      // after the loads are in flight
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int row = qd * 32 + hh * 16 + rr * 8 + g, mo = m0 + hh * 16 + rr * 8 + g;
+            const float4 e01 = *reinterpret_cast<const float4*>(xb + row * 4), e23 = *reinterpret_cast<const float4*>(xb + row * 4 + 2);
+            const float mean = 0.25f * ((e01.x + e01.z) + (e23.x + e23.z));
+            const float d0 = e01.x - mean, d1 = e01.z - mean, d2 = e23.x - mean, d3 = e23.z - mean;
+            const float dev = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+            const float rstd = rsqrtf(fmaf(n_w, dev, (e01.y + e01.w) + (e23.y + e23.w)) * inv_n + p.ln_eps);
+            if (mo < a.M) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                SmemIO<KIND>::st2(p.Cop, (size_t)mo * p.ldcop + col0 + 8 * c + 2 * q, (o[hh][rr][c].x - mean) * rstd, (o[hh][rr][c].y - mean) * rstd);
+            }
+          }
+      }
     };
 
     for (int j = gp; j < njobs; j += 2) {
@@ -547,9 +629,13 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
           mbar_arrive(&att_ready);
         }
         if (fused && h < 2 && k > 0) final_epilogue(k - 1);   // after this warp's first head of the next block (Z_LA = 2)
+        if (fused && cop_ln && (h == 2 || h == 3) && k > 0) ln_pass2(k - 1);   // one head later
       }
     }
-    if (fused && nk_cta > 0) final_epilogue(nk_cta - 1);
+    if (fused && nk_cta > 0) {
+      final_epilogue(nk_cta - 1);
+      if (cop_ln) ln_pass2(nk_cta - 1);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -565,7 +651,8 @@ static bool attn_frag_config(int d, int cross, int Cout, int* nst, int* stage_by
   const int BN = cross ? d : 3 * d;
   const size_t sj = tc::Z_ABYTES + (((size_t)BN * 128 + 1023) & ~(size_t)1023), so = Cout ? tc::Z_ABYTES + (size_t)Cout * 128 : 0;
   const size_t stage = sj > so ? sj : so;
-  const size_t stg = cross ? 0 : (size_t)tc::Z_EPI_WARPS * 16 * tc::Z_VLD * 4;
+  // warp-private v tiles (self) + the LayerNorm exchange buffer [2][128][4] (mean, M2) of the fused variant
+  const size_t stg = (cross ? 0 : (size_t)tc::Z_EPI_WARPS * 16 * tc::Z_VLD * 4) + (Cout ? 2 * tc::Z_TM * 4 * 8 : 0);
   int n = (int)((Z_SMEM_LIMIT - stg - 1024) / stage);
   if (n > tc::Z_MAXST) n = tc::Z_MAXST;
   if (n < 2) return false;
@@ -627,6 +714,7 @@ cudaError_t launch_attn_frag(const void* tmA, const void* tmB, const void* tmS, 
   const uint32_t fmt = tc::umma_fmt(kind);
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(tc::Z_TM >> 4) << 24);
   const uint32_t idesc_o = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(tc::Z_TM >> 4) << 24);
+  if (p.cop_ln && (a.cross || !p.fused || a.heads < 4 || !p.Cop || !p.C32)) return cudaErrorInvalidValue;   // second pass runs one head after the first
   const int nitems = ((a.M + tc::Z_TM - 1) / tc::Z_TM) * (p.fused ? 1 : a.heads);
   const int sms = attn_layer_sms();
   const unsigned grid = (unsigned)(nitems < sms ? nitems : sms);

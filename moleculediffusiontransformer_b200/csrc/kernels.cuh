@@ -244,6 +244,7 @@ struct AttnLayerParams {
   void* scratch;           // [SMs][attn_layer_slots(heads)][128][d] operand dtype: CTA-private head-output slots (L2 resident)
   int f16;                 // gemm_attn_frag.cu: attention core on f16 m16n8k16 MMAs (cross: K / V cache packed with kperm = 2)
   int l2_hint;             // scratch stores carry an L2 evict_last policy (MDT_L2_HINT=1; measured in profiles/README.md)
+  int cop_ln; float ln_eps;  // gemm_attn_frag.cu, fused: Cop = LayerNorm(C32 row) without affine (the next attention stage's operand)
   int fused;               // 1: out-projection inside the kernel; 0 (gemm_attn_frag.cu only): head outputs go to a.att, one work item per (row block, head)
   int nslot;               // filled by the launcher from here on
   int nst, stage_bytes, nacc; unsigned tmem_cols;

@@ -412,7 +412,7 @@ struct Builder {
   }
   void emit_attn_layer(std::vector<Op>& prog, const void* A, int C, int L, const float* dW32, const float* bias_q, int cross,
                        int cross_layer, const void* kn_flag, const void* kvf_c, const void* kvf_n, const float* dWo32,
-                       const float* bias_o, float* t, void* cop, bool fused = true) {
+                       const float* bias_o, float* t, void* cop, bool fused = true, bool cop_ln = false) {
     // fused == false: gemm_attn_frag.cu writes the head outputs to pl.att and the caller emits the out-projection GEMM itself
     Op op; op.type = OP_ATTN_LAYER; op.rps = L; op.cross = cross != 0; op.cross_layer = cross_layer;
     const int kch = pl.prec == MDT_PREC_TF32 ? 32 : 64;
@@ -444,6 +444,8 @@ struct Builder {
       memset(op.tmC, 0, sizeof op.tmC); memset(op.tmD, 0, sizeof op.tmD);
     }
     op.frag = fused ? frag_ok(C, L, cross) : true;
+    y.cop_ln = (cop_ln && op.frag) ? 1 : 0; y.ln_eps = 1e-5f;
+    if (cop_ln && !op.frag) raise(MDT_ERR_INVALID, "LayerNorm tail requested for an attention layer outside gemm_attn_frag.cu");
     // fp16 operands always take the f16 attention core (gemm_attn_frag.cu instantiates only that pairing)
     { const char* hf = getenv("MDT_ATTN_F16"); y.f16 = (op.frag && (pl.prec == MDT_PREC_F16 || !(hf && hf[0] == '0'))) ? 1 : 0; }
     if (cross && cross_layer >= 0) pl.cross[cross_layer].kperm = op.frag ? (y.f16 ? 2 : 1) : 0;
@@ -699,8 +701,10 @@ struct Builder {
         }
         const float* d_bo = upload(bo);
         if (layer_self) {
+          // with a cross-attention stage next, the fragment kernel's epilogue writes LayerNorm(t) for its q projection
+          cross_ln_done = has_cross && !prefix && heads >= 4 && frag_ok(C, L, 0) && !getenv("MDT_NO_LN_EPILOGUE") && !getenv("MDT_NO_ATTN_LN");
           emit_attn_layer(prog, tn, C, L, d_wr_self, d_bq_self, 0, -1, nullptr, nullptr, nullptr, d_wo, d_bo, t,
-                          has_cross ? nullptr : (void*)tn);
+                          (!has_cross || cross_ln_done) ? (void*)tn : nullptr, true, cross_ln_done);
         } else if (fast) {
           // without a cross-attention stage the raw operand copy of the new token stream feeds FF1 directly; with one, the epilogue
           // writes LayerNorm(t) for its q projection (not at the end of the CFG prefix: the null-branch rows are replicated there)
@@ -1103,7 +1107,7 @@ static std::string describe(const Op& op, int Beff) {
     case OP_GEMM_TMA: snprintf(b, sizeof b, "gemm_tma  M=%d N=%d K=%dx%d L=%d bn=%d%s%s%s%s", Beff * op.rps, op.tg.N, op.tg.taps, op.tg.C, op.tg.L, op.tg.BN,
                                op.tg.gn_L ? " +gn" : "", op.tg.res ? " +res" : "", op.tg.act ? " +act" : (op.tg.cop_ln ? " +ln" : ""), h); break;
     case OP_GEMM_ATTN: snprintf(b, sizeof b, "gemm_attn%s %s M=%d C=%d L=%d%s", op.umma_core ? "_umma" : "", op.cross ? "cross" : "self", Beff * op.rps, op.gat.C, op.gat.L, h); break;
-    case OP_ATTN_LAYER: snprintf(b, sizeof b, "attn_%s%s %s M=%d C=%d L=%d%s%s", op.frag ? "frag " : "layer", op.al.fused ? "" : "(unfused)", op.cross ? "cross" : "self", Beff * op.rps, op.al.a.C, op.al.a.L, op.al.Cop ? " +cop" : "", h); break;
+    case OP_ATTN_LAYER: snprintf(b, sizeof b, "attn_%s%s %s M=%d C=%d L=%d%s%s", op.frag ? "frag " : "layer", op.al.fused ? "" : "(unfused)", op.cross ? "cross" : "self", Beff * op.rps, op.al.a.C, op.al.a.L, op.al.cop_ln ? " +ln" : (op.al.Cop ? " +cop" : ""), h); break;
     case OP_RESNET_SMALL: snprintf(b, sizeof b, "resnet_small %s B=%d L=%d %d->%d%s", op.rs.mode ? "head" : "full", Beff, op.rs.L, op.rs.Cin, op.rs.Cout, h); break;
     case OP_GEMM: snprintf(b, sizeof b, "gemm      M=%d N=%d K=%d taps=%d stride=%d%s", Beff * op.rps, op.g.N, op.g.K, op.g.a.taps, op.g.a.stride, h); break;
     case OP_GN_APPLY: snprintf(b, sizeof b, "gn_apply  B=%d L=%d C=%d%s%s", Beff, op.ga.L, op.ga.c0 + op.ga.c1, op.ga.raw ? " +raw" : "", h); break;
