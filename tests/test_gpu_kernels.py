@@ -45,6 +45,32 @@ def test_linear_against_float64(prec, act):
     assert ran >= 5
 
 
+def test_fp16_operands_saturate_and_keep_small_values():
+    """precision='fp16' converts operands with cvt.rn.satfinite: an activation beyond the fp16 range clamps to +-65504 (finite result,
+    no inf / nan anywhere), and values far below the fp16 normal range only lose absolute precision (<= 2^-25 per operand)."""
+    from moleculediffusiontransformer_b200 import _capi
+
+    lib = _capi.load()
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 256, 128, 128
+    a = torch.randn(M, K, generator=g)
+    a[0, 0], a[1, 1] = 1e6, -3e5                       # outside the fp16 range
+    a[2] = a[2] * 1e-6                                 # a row of subnormal-range values
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ad, wd = a.cuda(), w.cuda()
+    rc = lib.mdt_op_linear(ad.data_ptr(), wd.data_ptr(), None, None, out.data_ptr(), M, N, K, 0, _capi.PRECISIONS["fp16"], None)
+    torch.cuda.synchronize()
+    assert rc == 0, lib.mdt_last_error()
+    out = out.cpu()
+    assert torch.isfinite(out).all()
+    sat = a.clamp(-65504.0, 65504.0)
+    want = sat.double() @ w.double().T
+    assert _rel(out[3:], want[3:]) < TOL["fp16"]                       # ordinary rows: unaffected
+    assert _rel(out[:2], want[:2]) < TOL["fp16"]                       # saturated operands behave as +-65504
+    assert float((out[2].double() - want[2]).abs().max()) < K * 2.0 ** -25 * float(w.abs().max()) * 1.5
+
+
 def test_linear_empty_is_noop():
     from moleculediffusiontransformer_b200 import _capi
 
