@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ __align__(8) uint64_t att_ready, out_full, out_empty;
+  __shared__ __align__(8) uint64_t a_full, a_empty;  // resident activation tile (p.ares_bytes != 0)
   __shared__ __align__(8) uint64_t ln_bar[4];       // cop_ln: per TMEM lane quadrant, "row statistics of this block are in shared memory"
   __shared__ uint32_t tmem_base_s;
 
@@ -162,6 +163,13 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
   const int heads = a.heads, d = a.d;
   const int BN = CROSS ? d : 3 * d;
   const int NST = p.nst, stage_bytes = p.stage_bytes;
+  // Resident activation tile: the 128 x C operand tile of a row block is loaded ONCE into its own region and serves the projections of
+  // all heads of the block (fused: the eight heads in sequence; per-head variant: a CTA owns a contiguous item range, so consecutive
+  // items share the block) instead of being re-streamed through L2 with every head's weight slice.  The stages then carry only the
+  // weight chunk (at offset 0) for projections; out-projection chunks keep [scratch A | W_o].  Chosen by the launcher where it fits.
+  const bool ares = p.ares_bytes != 0;
+  uint8_t* const stg0 = smem + p.ares_bytes;     // stage ring behind the resident tile
+  const int boff = ares ? 0 : Z_ABYTES;          // weight chunk offset inside a projection stage
   const int Cout = p.Cout;
   const int nblk = (a.M + Z_TM - 1) / Z_TM;
   const int cph = d / KCH;
@@ -171,9 +179,13 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
   // what balances short levels (256 row blocks on 148 SMs) across the grid
   const bool fused = p.fused != 0;
   const int nitems = fused ? nblk : nblk * heads;
-  const int nk_cta = (int)blockIdx.x < nitems ? (nitems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // per-head variant with a resident tile: contiguous item ranges (items of one row block are consecutive); otherwise round robin
+  const bool contig = ares && !fused;
+  const int it_lo = contig ? (int)(((long long)blockIdx.x * nitems) / (int)gridDim.x) : 0;
+  const int it_hi = contig ? (int)(((long long)(blockIdx.x + 1) * nitems) / (int)gridDim.x) : 0;
+  const int nk_cta = contig ? it_hi - it_lo : ((int)blockIdx.x < nitems ? (nitems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0);
   const int njobs = fused ? nk_cta * heads : nk_cta;
-  auto item_of_k = [&](int k) { const int b = (int)blockIdx.x + k * (int)gridDim.x; return a.rev ? nitems - 1 - b : b; };
+  auto item_of_k = [&](int k) { const int b = contig ? it_lo + k : (int)blockIdx.x + k * (int)gridDim.x; return a.rev ? nitems - 1 - b : b; };
   auto block_of_k = [&](int k) { return item_of_k(k); };      // fused mode: item == row block
 
   if (tid == 0) {
@@ -182,6 +194,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
     mbar_init(&att_ready, Z_EPI_WARPS * 32);
     mbar_init(&out_full, 1);
     mbar_init(&out_empty, Z_EPI_WARPS);
+    mbar_init(&a_full, 1); mbar_init(&a_empty, 1);
     for (int s = 0; s < 4; ++s) mbar_init(&ln_bar[s], 4);      // the four warps that share a quadrant's rows (column quarters)
     fence_barrier_init();
   }
@@ -207,7 +220,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
         const int j0 = kk * heads;
         for (int oc = 0; oc < ochunks; ++oc) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sa = stg0 + stage * stage_bytes;
           mbar_arrive_expect_tx(&full_bar[stage], tx_o);
           const int hh = oc / cph, sub = oc - hh * cph;
           const int slot = (j0 + hh) % p.nslot;
@@ -217,16 +230,27 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
         }
       };
       int k = 0, h = 0;
+      int cur_blk = -1, n_a = 0;                    // resident tile: row block it holds, tiles loaded so far
       for (int j = 0; j < njobs; ++j) {
         int blk;
         if (fused) { blk = block_of_k(k); if (h == Z_LA && k > 0) load_out(k - 1); }
         else { const int it = item_of_k(j); blk = it / heads; h = it - blk * heads; }
+        if (ares && blk != cur_blk) {
+          if (n_a > 0) mbar_wait(&a_empty, (uint32_t)(n_a - 1) & 1u);        // every MMA that read the previous tile has completed
+          mbar_arrive_expect_tx(&a_full, (uint32_t)(a.kchunks * Z_ABYTES));
+          for (int kc = 0; kc < a.kchunks; ++kc) tma_load_3d(smem + kc * Z_ABYTES, &tmA, &a_full, kc * KCH, 0, blk * a.Sb);
+          cur_blk = blk; ++n_a;
+        }
         for (int kc = 0; kc < a.kchunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sa = smem + stage * stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[stage], tx_j);
-          tma_load_3d(sa, &tmA, &full_bar[stage], kc * KCH, 0, blk * a.Sb);
-          tma_load_2d(sa + Z_ABYTES, &tmB, &full_bar[stage], kc * KCH, h * BN);
+          uint8_t* sa = stg0 + stage * stage_bytes;
+          if (ares) {
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(BN * 128));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], tx_j);
+            tma_load_3d(sa, &tmA, &full_bar[stage], kc * KCH, 0, blk * a.Sb);
+          }
+          tma_load_2d(sa + boff, &tmB, &full_bar[stage], kc * KCH, h * BN);
           if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
         if (fused && ++h == heads) { h = 0; ++k; }
@@ -244,7 +268,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sa = smem_u32(stg0 + stage * stage_bytes);
           const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + Z_ABYTES);
 #pragma unroll
           for (int kq = 0; kq < 4; ++kq)
@@ -257,9 +281,17 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
       }
     };
     int k = 0, h = 0;
+    int cur_blk = -1, m_a = 0;
+    const uint32_t ares_u32 = smem_u32(smem);
     for (; j < njobs; ++j) {
       {
         if (fused && h == Z_LA && k > 0) mma_out(k - 1);
+        int blk = 0; bool last_use = false;
+        if (ares) {
+          if (fused) { blk = block_of_k(k); last_use = h == heads - 1; }
+          else { blk = item_of_k(j) / heads; last_use = j == njobs - 1 || item_of_k(j + 1) / heads != blk; }
+          if (blk != cur_blk) { mbar_wait(&a_full, (uint32_t)m_a & 1u); tc_fence_after(); cur_blk = blk; ++m_a; }
+        }
         const int buf = j & 1;
         mbar_wait(&acc_empty[buf], ((uint32_t)(j >> 1) & 1u) ^ 1u);
         tc_fence_after();
@@ -268,13 +300,16 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-            const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + Z_ABYTES);
+            const uint32_t sa = smem_u32(stg0 + stage * stage_bytes);
+            const uint64_t adesc = make_desc(ares ? ares_u32 + (uint32_t)(k0 * Z_ABYTES) : sa), bdesc = make_desc(sa + (uint32_t)boff);
 #pragma unroll
             for (int kq = 0; kq < 4; ++kq)
               umma<KIND>(tmem_d, adesc + (uint64_t)(2 * kq), bdesc + (uint64_t)(2 * kq), idesc, (uint32_t)((k0 | kq) != 0));
             umma_commit(&empty_bar[stage]);
-            if (k0 == a.kchunks - 1) umma_commit(&acc_full[buf]);
+            if (k0 == a.kchunks - 1) {
+              umma_commit(&acc_full[buf]);
+              if (last_use) umma_commit(&a_empty);      // the resident tile may be replaced once these MMAs have completed
+            }
           }
           __syncwarp();
           if (++stage == NST) { stage = 0; phase ^= 1u; }
@@ -293,7 +328,8 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
     const int g = lane >> 2, q = lane & 3;
     const int L = a.L;
     const int bm = (!CROSS && L < 16) ? ~(L - 1) : 0;
-    float* vt = reinterpret_cast<float*>(smem + NST * stage_bytes) + (size_t)ew * 16 * Z_VLD;   // warp-private v tile (self only)
+    constexpr int VT_BYTES = F16 ? 64 * VKP * 2 : 16 * Z_VLD * 4;      // warp-private v tile (self only): f16 [64 features][24], tf32 [16 keys][68]
+    float* vt = reinterpret_cast<float*>(stg0 + NST * stage_bytes + (size_t)ew * VT_BYTES);
     const size_t cta_slot0 = (size_t)blockIdx.x * p.nslot;
     const uint32_t lane_addr = (uint32_t)r16 << 16;
     const int sub = gp * 2 + half;          // this warp's column quarter of the OUT tile (four warps per quadrant)
@@ -302,7 +338,7 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
     // column quarter per row in shared memory, double buffered by block parity; second pass (ln_pass2) one head later -- by then the
     // other warp group has long finished its first pass, so the mbarrier wait costs nothing -- merges the four quarters and normalises
     // the values it re-reads from its own C32 stores.
-    float2* xch = reinterpret_cast<float2*>(smem + NST * stage_bytes + (CROSS ? 0 : (size_t)Z_EPI_WARPS * 16 * Z_VLD * 4));   // [2][128][4]
+    float2* xch = reinterpret_cast<float2*>(stg0 + NST * stage_bytes + (CROSS ? 0 : (size_t)Z_EPI_WARPS * VT_BYTES));   // [2][128][4]
     const bool cop_ln = !CROSS && p.cop_ln != 0;     // self-attention layers only (the cross layer hands FeedForward a raw copy)
 
     auto final_epilogue = [&](int kk) {
@@ -646,20 +682,36 @@ __global__ void __launch_bounds__(Z_THREADS, 1) attn_frag_kernel(const __grid_co
 
 static const size_t Z_SMEM_LIMIT = 232448 - 1024;
 
-// Cout = 0: unfused (no out-projection accumulator, no out-projection stages)
-static bool attn_frag_config(int d, int cross, int Cout, int* nst, int* stage_bytes, unsigned* tmem_cols, size_t* smem) {
+// Cout = 0: unfused (no out-projection accumulator, no out-projection stages).  tile_bytes = 128 x C operand bytes of a row block's
+// activation tile: kept resident (ares_bytes = tile_bytes) when at least three weight-only stages still fit beside it, else streamed
+// with every head's weight slice as before (ares_bytes = 0).  f16core: the f16 attention core needs 3 KB of v tile per warp, not 4.25.
+static bool attn_frag_config(int d, int cross, int Cout, size_t tile_bytes, int f16core, int* nst, int* stage_bytes, unsigned* tmem_cols,
+                             size_t* smem, int* ares_bytes) {
+  static const bool no_res = getenv("MDT_NO_A_RESIDENT") != nullptr;
   const int BN = cross ? d : 3 * d;
-  const size_t sj = tc::Z_ABYTES + (((size_t)BN * 128 + 1023) & ~(size_t)1023), so = Cout ? tc::Z_ABYTES + (size_t)Cout * 128 : 0;
-  const size_t stage = sj > so ? sj : so;
+  const size_t bj = ((size_t)BN * 128 + 1023) & ~(size_t)1023, so = Cout ? tc::Z_ABYTES + (size_t)Cout * 128 : 0;
   // warp-private v tiles (self) + the LayerNorm exchange buffer [2][128][4] (mean, M2) of the fused variant
-  const size_t stg = (cross ? 0 : (size_t)tc::Z_EPI_WARPS * 16 * tc::Z_VLD * 4) + (Cout ? 2 * tc::Z_TM * 4 * 8 : 0);
-  int n = (int)((Z_SMEM_LIMIT - stg - 1024) / stage);
-  if (n > tc::Z_MAXST) n = tc::Z_MAXST;
-  if (n < 2) return false;
+  const size_t vt = f16core ? 64 * 24 * 2 : 16 * tc::Z_VLD * 4;
+  const size_t stg = (cross ? 0 : (size_t)tc::Z_EPI_WARPS * vt) + (Cout ? 2 * tc::Z_TM * 4 * 8 : 0);
   if (Cout + 2 * BN > 512) return false;                  // two projection accumulators (one per warp group) + OUT
   unsigned cols = 32;
   while ((int)cols < Cout + 2 * BN) cols <<= 1;
-  *nst = n; *stage_bytes = (int)stage; *tmem_cols = cols; *smem = (size_t)n * stage + stg + 1024;
+  *tmem_cols = cols;
+  if (!no_res && tile_bytes > 0 && tile_bytes + stg + 1024 < Z_SMEM_LIMIT) {
+    const size_t stage = bj > so ? bj : so;
+    int n = (int)((Z_SMEM_LIMIT - tile_bytes - stg - 1024) / stage);
+    if (n > tc::Z_MAXST) n = tc::Z_MAXST;
+    if (n >= 3) {
+      *nst = n; *stage_bytes = (int)stage; *ares_bytes = (int)tile_bytes; *smem = tile_bytes + (size_t)n * stage + stg + 1024;
+      return true;
+    }
+  }
+  const size_t sj = tc::Z_ABYTES + bj;
+  const size_t stage = sj > so ? sj : so;
+  int n = (int)((Z_SMEM_LIMIT - stg - 1024) / stage);
+  if (n > tc::Z_MAXST) n = tc::Z_MAXST;
+  if (n < 2) return false;
+  *nst = n; *stage_bytes = (int)stage; *ares_bytes = 0; *smem = (size_t)n * stage + stg + 1024;
   return true;
 }
 
@@ -670,8 +722,8 @@ bool attn_frag_supported(int kind, int C, int L, int heads, int d, int cross, in
   if (d != 64 || heads < 2 || (heads & 1) || C % kch) return false;
   if (!(L == 4 || L == 8 || L == 16)) return false;
   if (Cout != 0 && (Cout < 128 || Cout > 256 || Cout % 128)) return false;   // four column quarters of >= 32 columns
-  int nst, sb; unsigned tc_; size_t sm;
-  return attn_frag_config(d, cross, Cout, &nst, &sb, &tc_, &sm);
+  int nst, sb, ar; unsigned tc_; size_t sm;
+  return attn_frag_config(d, cross, Cout, 0, 0, &nst, &sb, &tc_, &sm, &ar);     // the streaming layout with the larger v tiles is the tighter fit
 }
 
 typedef void (*AttnFragKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnLayerParams,
@@ -706,7 +758,8 @@ cudaError_t launch_attn_frag(const void* tmA, const void* tmB, const void* tmS, 
   if (a.M <= 0) return cudaSuccess;
   size_t smem = 0;
   if (!p.fused) p.Cout = 0;
-  if (!attn_frag_config(a.d, a.cross, p.Cout, &p.nst, &p.stage_bytes, &p.tmem_cols, &smem)) return cudaErrorInvalidValue;
+  const size_t tile_bytes = (size_t)tc::Z_TM * a.C * (kind == 1 ? 4 : 2);
+  if (!attn_frag_config(a.d, a.cross, p.Cout, tile_bytes, p.f16, &p.nst, &p.stage_bytes, &p.tmem_cols, &smem, &p.ares_bytes)) return cudaErrorInvalidValue;
   if (a.cross && !a.kvf_c) return cudaErrorInvalidValue;
   p.nacc = 2;
   p.nslot = a.heads + tc::Z_LA;

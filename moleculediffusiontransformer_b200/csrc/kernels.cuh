@@ -248,6 +248,7 @@ struct AttnLayerParams {
   int fused;               // 1: out-projection inside the kernel; 0 (gemm_attn_frag.cu only): head outputs go to a.att, one work item per (row block, head)
   int nslot;               // filled by the launcher from here on
   int nst, stage_bytes, nacc; unsigned tmem_cols;
+  int ares_bytes;          // gemm_attn_frag.cu: bytes of the resident activation tile in front of the stage ring (0: streamed per head)
 };
 bool attn_layer_supported(int kind, int C, int L, int heads, int d, int cross, int Cout);
 size_t attn_layer_scratch_bytes(int kind, int heads, int d);

@@ -62,7 +62,7 @@ def test_unet_eval_umma_attention_core_everywhere(name, prec, model_cache, monke
                                  {"MDT_FUSED_LAYER_MAXC": "256", "MDT_ATTN_FRAG": "0"},
                                  # tf32 m16n8k8 attention core instead of f16 m16n8k16 (and the tf32 K / V fragment cache), narrow tiles
                                  {"MDT_ATTN_F16": "0"}, {"MDT_ATTN_F16": "0", "MDT_FUSED_LAYER_MAXC": "256"}, {"MDT_NO_WIDE_BN": "1"},
-                                 {"MDT_L2_HINT": "1"}, {"MDT_NO_LN_EPILOGUE": "1"}, {"MDT_NO_ATTN_LN": "1"}, {"MDT_PDL": "3"}])
+                                 {"MDT_L2_HINT": "1"}, {"MDT_NO_LN_EPILOGUE": "1"}, {"MDT_NO_ATTN_LN": "1"}, {"MDT_PDL": "3"}, {"MDT_NO_A_RESIDENT": "1"}])
 def test_unet_eval_with_a_fast_path_switched_off(env, prec, model_cache, monkeypatch):
     """Every attention mode of the fused kernel stays reachable and correct: cp.async-staged cross-attention and per-sample
     self-attention at L = 4 (the defaults pack those), the packed cross path limited to the short levels, the unfused
