@@ -281,3 +281,25 @@ def test_training_forward_delegates_to_a_reference_object():
     m.set_training_delegate(ref)
     loss = m(torch.zeros(2, 12), torch.ones(2, 16, 64))
     assert float(loss) == 1.0 and set(ref.loaded) == set(m.state_dict())
+
+
+def test_precision_table_matches_the_c_header_and_defaults(monkeypatch):
+    """The Python precision names map to the enum values of include/mdt_b200.h; the default mode is the fp16-operand one and the
+    chunk size falls back to 4096 rows without a device (32 rows per SM with one), MDT_MAX_BATCH / MDT_PRECISION override both."""
+    import re
+
+    from moleculediffusiontransformer_b200 import _capi
+    from moleculediffusiontransformer_b200 import plan as planmod
+
+    hdr = open(os.path.join(ROOT, "include", "mdt_b200.h")).read()
+    enum = {m.group(1): int(m.group(2)) for m in re.finditer(r"MDT_PREC_(\w+)\s*=\s*(\d+)", hdr)}
+    assert enum == {"FP32": 0, "TF32": 1, "BF16": 2, "F16": 3}
+    assert _capi.PRECISIONS == {"fp32": 0, "tf32": 1, "bf16": 2, "fp16": 3}
+    monkeypatch.delenv("MDT_PRECISION", raising=False)
+    monkeypatch.delenv("MDT_MAX_BATCH", raising=False)
+    assert planmod.default_precision() == "fp16"
+    if not torch.cuda.is_available():
+        assert planmod.default_max_batch() == 4096
+    monkeypatch.setenv("MDT_PRECISION", "tf32")
+    monkeypatch.setenv("MDT_MAX_BATCH", "1024")
+    assert planmod.default_precision() == "tf32" and planmod.default_max_batch() == 1024
