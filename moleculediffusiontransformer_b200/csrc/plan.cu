@@ -1134,6 +1134,12 @@ static void dump_op_times() {
 static void run_program(mdt_plan& pl, std::vector<Op>& prog, int Beff, int n_cond, int n_ctx, cudaStream_t s) {
   if (getenv("MDT_NO_SHARED_PREFIX")) for (Op& op : prog) op.half = false;
   const int Beff_full = Beff;
+  // programmatic dependent launch only where every grid of the program leaves SMs free (launch.cuh): row blocks of the longest level
+  {
+    static int sms = 0;
+    if (sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    pdl_auto() = ((long long)Beff_full * pl.L0 + 127) / 128 < sms ? 1 : 0;
+  }
   const bool timed = op_times_on();
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (timed) { CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); }
