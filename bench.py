@@ -363,7 +363,8 @@ def run_ours(args):
                              "dram__bytes of every kernel of one pass"},
     }
     also = []
-    for other in [a for a in args.also.split(",") if a and a != args.precision]:
+    # (N = 1 only: under torchrun the other ranks have left by now, and the per-GPU alternatives do not change with N)
+    for other in [a for a in args.also.split(",") if a and a != args.precision and world == 1]:
         # secondary arithmetic modes, same workload, device-resident timing only (reported beside the headline)
         plan2 = model._plan_for(dev, other, batch=B, timesteps=T)
         def step2(i):
